@@ -1,0 +1,109 @@
+/*
+ * movii_b200 — C ABI of the B200-native (sm_100a) DiT / WanVAE hot path.
+ *
+ * The reference (ZulutionAI/MoviiGen1.1) is pure Python and has no FFI; each entry point below
+ * replaces the library call the reference makes at the cited call site (paths relative to the
+ * reference repo).  Conventions:
+ *   - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller (PyTorch);
+ *     the library never allocates device memory and never synchronises the device;
+ *   - every launch goes to the caller-supplied stream (a cudaStream_t passed as void*);
+ *   - return value: MV_OK (0) or a negative MV_E_* code; the message is in mv_last_error()
+ *     (thread-local);  no exceptions, no exit();
+ *   - the library refuses to run on anything that is not compute capability 10.x
+ *     (MV_E_ARCH) — there is no fallback path of any kind.
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef MOVII_B200_H_
+#define MOVII_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MV_OK 0
+#define MV_E_SHAPE (-1)
+#define MV_E_ARCH (-2)
+#define MV_E_CUDA (-3)
+#define MV_E_NCCL (-4)
+#define MV_E_WORKSPACE (-5)
+
+typedef void* mv_stream_t; /* cudaStream_t */
+
+/* GEMM epilogues (mv_gemm_bf16). acc = fp32 accumulator, y = bf16(acc + bias) as nn.Linear under
+ * bf16 autocast returns it. */
+#define MV_EPI_BF16 0       /* out_bf16[m,n]  = y                                   (model.py:139-141,171-173) */
+#define MV_EPI_BF16_GELU 1  /* out_bf16[m,n]  = bf16(gelu_tanh(float(y)))           (model.py:267-268)         */
+#define MV_EPI_RESID_F32 2  /* out_f32[m,n]  += float(y) * (gate ? gate[n] : 1)     (model.py:302,306,309)     */
+#define MV_EPI_F32_ROUND 3  /* out_f32[m,n]   = float(y)                            (model.py:529)             */
+
+const char* mv_last_error(void);
+int mv_version(void);
+/* MV_OK when the current device is sm_100 (B200); MV_E_ARCH otherwise; MV_E_CUDA if no device. */
+int mv_device_check(void);
+
+/* ---- dense contractions ---------------------------------------------------------------------- */
+
+/* out = epilogue(A[M,K] . W[N,K]^T + bias[N]); A, W bf16 (K contiguous, lda/ldw in elements,
+ * multiples of 8), fp32 accumulate on tcgen05 tensor cores.  Replaces nn.Linear under bf16 autocast
+ * (cuBLASLt) at wan/modules/model.py:139-141,155,171-173,180,267-269,451-453 and the patch-embedding
+ * Conv3d at :445-450,529.  bias may be NULL; gate (fp32[N]) only for MV_EPI_RESID_F32, may be NULL. */
+int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                 int64_t ldo, const float* gate, int M, int N, int K, int epilogue, mv_stream_t stream);
+
+/* o[Lq,H,128] = softmax(q k^T * scale) v, non-causal, bf16 in/out, fp32 softmax and accumulation;
+ * q,k,v,o are [L, H, 128] views with row strides ldq/ldk/ldv/ldo (elements) and heads contiguous
+ * (head h at column offset h*128).  Keys/values are rows [0, Lk).  Replaces
+ * flash_attn.flash_attn_varlen_func at wan/modules/attention.py:113-127 (self- and cross-attention,
+ * model.py:146-151,176). */
+int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     void* o, int64_t ldo, int Lq, int Lk, int H, float softmax_scale, mv_stream_t stream);
+
+/* ---- HBM-bound fused row kernels -------------------------------------------------------------- */
+
+/* out_bf16[m,:] = bf16( LN(x[m,:]) [*w + b] [rounded to bf16 if round_ln] * (1 + scale) + shift ).
+ * LN is affine-free unless w/b given; fp32 statistics, eps as given.  shift/scale may be NULL (no
+ * modulation).  Replaces WanLayerNorm + adaLN modulation + autocast input cast,
+ * wan/modules/model.py:89-99,299,306,307. */
+int mv_ln_modulate(const float* x, int64_t ldx, const float* shift, const float* scale, const float* w,
+                   const float* b, void* out_bf16, int64_t ldo, int M, int C, float eps, int round_ln,
+                   mv_stream_t stream);
+
+/* In place on a bf16 [M, C] slab (row stride ld): full-row WanRMSNorm (fp32 stats, bf16 rounding
+ * before the weight multiply, model.py:70-86) followed, when cs != NULL, by 3-axis RoPE on
+ * interleaved pairs with a per-token cos/sin table cs[M][head_dim/2][2] fp32 (model.py:39-67;
+ * xdit_context_parallel.py:24-62 for the rank-offset table), output rounded to bf16
+ * (attention.py:59-83). */
+int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, const float* cs, int M, int C,
+                    int head_dim, float eps, mv_stream_t stream);
+
+/* A_bf16[L, C*ph*pw] <- latent fp32 [C, F, H, W], patch (1,ph,pw); column = c*ph*pw + i*pw + j, the
+ * flatten(1) order of patch_embedding.weight (model.py:445-450,529-533). */
+int mv_patchify(const float* latent, void* a_bf16, int C, int F, int H, int W, int ph, int pw,
+                mv_stream_t stream);
+
+/* Head (model.py:333-343) + unpatchify (:581-609), all fp32:
+ * out[c, f, h*ph+i, w*pw+j] = sum_k (LN(x[n,:])*(1+scale)+shift)[k] * Wh[(i*pw+j)*Cout + c, k] + bh[..]
+ * for token n = (f,h,w) < F*Hp*Wp. */
+int mv_head_unpatchify(const float* x, int64_t ldx, const float* shift, const float* scale, const float* Wh,
+                       const float* bh, float* out, int F, int Hp, int Wp, int ph, int pw, int Cout, int C,
+                       float eps, mv_stream_t stream);
+
+/* out[N] = W[N,K] . act(x[K]) + b[N], fp32 (M = 1).  act_in: 0 none, 1 SiLU.  Replaces the fp32
+ * time_embedding / time_projection Linears (model.py:455-457,541-545). */
+int mv_linear_f32_vec(const float* x, const float* W, const float* b, float* out, int N, int K, int act_in,
+                      mv_stream_t stream);
+
+/* out[dim] = cat(cos(t*w_i), sin(t*w_i)), w_i = 10000^(-i/(dim/2)), computed in fp64, stored fp32
+ * (sinusoidal_embedding_1d, model.py:15-25).  t: device int64/fp32 scalar. */
+int mv_sinusoid_embed(const void* t, int t_is_int64, float* out, int dim, mv_stream_t stream);
+
+/* ---- WanVAE decoder (wan/modules/vae.py) ------------------------------------------------------- */
+/* declared in the VAE section of the library when built; see DESIGN.md for status. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVII_B200_H_ */

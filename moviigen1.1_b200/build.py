@@ -1,0 +1,78 @@
+"""Builds lib/libmovii_b200.so (the C-ABI library, include/movii_b200.h) with nvcc for sm_100a.
+
+In-tree build: the .so travels to the GPU box with the repo snapshot.  No torch involvement.
+Usage: python build.py [--force] [--verbose]
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libmovii_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest(src):
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cuh", ".h")) or f == src:
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(fh.read())
+    with open(os.path.join(HERE, "..", "include", "movii_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src, force, verbose):
+    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    stamp = obj + ".sha"
+    dig = _digest(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return obj, False, ""
+    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    return obj, True, r.stderr
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJDIR, exist_ok=True)
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
+    objs = [r[0] for r in results]
+    rebuilt = any(r[1] for r in results)
+    log = "\n".join(r[2] for r in results if r[2])
+    if log:
+        with open(os.path.join(LIBDIR, "ptxas.log"), "w") as fh:
+            fh.write(log)
+        if verbose:
+            print(log)
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,305 @@
+// tcgen05 GEMM for the DiT linears: out = epilogue(A[M,K] . W[N,K]^T + bias).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (A tile 128x64, W tile 256x64 per stage, 128B-swizzled, 4-stage ring)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1 M=128 N=256 K=16,
+//                               fp32 accumulators in TMEM, 2 accumulator stages = 512 columns)
+//   warps 2..5  epilogue       (tcgen05.ld -> bias / GELU / gate+residual -> global), overlapped
+//                               with the next tile's main loop through the 2 TMEM stages
+// Tile order is grouped (16 M-tiles x all N-tiles) so that a wave's working set stays in L2.
+//
+// Replaces nn.Linear under bf16 autocast (cuBLASLt) — wan/modules/model.py:139-141,155,171-173,180,
+// 267-269,451-453 — and the patch-embedding Conv3d (:445-450,529).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mv {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kGroupM = 16;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2;  // 16 KB
+constexpr uint32_t kBBytes = BN * BK * 2;  // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kGemmSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  const float* bias;
+  const float* gate;
+  void* out;
+  int64_t ldo;
+  int M, N, K;
+  int num_m, num_n, num_tiles, num_kb;
+};
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+  const int per_group = kGroupM * p.num_n;
+  const int g = tile / per_group;
+  const int within = tile - g * per_group;
+  const int gm = min(kGroupM, p.num_m - g * kGroupM);
+  m_blk = g * kGroupM + within % gm;
+  n_blk = within / gm;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kStageBytes);
+          tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB + stage * kBBytes, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sA + stage * kABytes));
+          const uint64_t bdesc = make_desc_kmajor_sw128(smem_u32(sB + stage * kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (>>4 = 2) per K=16 step inside the 128B swizzle atom
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c * 32, r);
+        tc_wait_ld();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float b = 0.f;
+            if (p.bias != nullptr && col0 + i < p.N) b = __ldg(p.bias + col0 + i);
+            v[i] = bf16_round(__uint_as_float(r[i]) + b);
+          }
+          const bool full_chunk = (col0 + 32 <= p.N);
+          if constexpr (EPI == MV_EPI_BF16 || EPI == MV_EPI_BF16_GELU) {
+            if constexpr (EPI == MV_EPI_BF16_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
+            if (full_chunk) {
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+                w.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+                w.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+                w.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+                o4[i] = w;
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
+            if (full_chunk) {
+              float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 w;
+                if constexpr (EPI == MV_EPI_RESID_F32) {
+                  float4 x = o4[i];
+                  float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
+                  if (p.gate != nullptr) {
+                    float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + col0) + i);
+                    g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
+                  }
+                  w.x = x.x + v[4 * i + 0] * g0;
+                  w.y = x.y + v[4 * i + 1] * g1;
+                  w.z = x.z + v[4 * i + 2] * g2;
+                  w.w = x.w + v[4 * i + 3] * g3;
+                } else {
+                  w.x = v[4 * i + 0]; w.y = v[4 * i + 1]; w.z = v[4 * i + 2]; w.w = v[4 * i + 3];
+                }
+                o4[i] = w;
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
+                if constexpr (EPI == MV_EPI_RESID_F32) {
+                  float g = p.gate != nullptr ? __ldg(p.gate + col0 + i) : 1.f;
+                  o[i] = o[i] + v[i] * g;
+                } else {
+                  o[i] = v[i];
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kGemmSmem)));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  gemm_bf16_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  MV_CHECK_LAUNCH("gemm_bf16_kernel");
+  return MV_OK;
+}
+
+}  // namespace mv
+
+extern "C" int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                            int64_t ldo, const float* gate, int M, int N, int K, int epilogue,
+                            mv_stream_t stream) {
+  using namespace mv;
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(M > 0 && N > 0 && K > 0, "mv_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  MV_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "mv_gemm_bf16: K/lda/ldw must be multiples of 8 (K=%d lda=%lld ldw=%lld)",
+             K, (long long)lda, (long long)ldw);
+  MV_REQUIRE(lda >= K && ldw >= K && ldo >= N, "mv_gemm_bf16: leading dimensions too small");
+  MV_REQUIRE(epilogue >= 0 && epilogue <= 3, "mv_gemm_bf16: unknown epilogue %d", epilogue);
+  const bool f32_out = (epilogue == MV_EPI_RESID_F32 || epilogue == MV_EPI_F32_ROUND);
+  MV_REQUIRE(ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "mv_gemm_bf16: output must be 16-byte aligned with 16-byte aligned rows");
+  MV_REQUIRE(gate == nullptr || (reinterpret_cast<uintptr_t>(gate) & 15) == 0, "mv_gemm_bf16: gate must be 16B aligned");
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t str[2] = {2, static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {BK, BM};
+    rc = make_tmap_bf16(&tmA, A, 2, dims, str, box, true);
+    if (rc != MV_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t str[2] = {2, static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {BK, BN};
+    rc = make_tmap_bf16(&tmB, W, 2, dims, str, box, true);
+    if (rc != MV_OK) return rc;
+  }
+  GemmParams p;
+  p.bias = bias;
+  p.gate = gate;
+  p.out = out;
+  p.ldo = ldo;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m = (M + BM - 1) / BM;
+  p.num_n = (N + BN - 1) / BN;
+  p.num_tiles = p.num_m * p.num_n;
+  p.num_kb = (K + BK - 1) / BK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case MV_EPI_BF16: return launch_gemm<MV_EPI_BF16>(tmA, tmB, p, st);
+    case MV_EPI_BF16_GELU: return launch_gemm<MV_EPI_BF16_GELU>(tmA, tmB, p, st);
+    case MV_EPI_RESID_F32: return launch_gemm<MV_EPI_RESID_F32>(tmA, tmB, p, st);
+    default: return launch_gemm<MV_EPI_F32_ROUND>(tmA, tmB, p, st);
+  }
+}

@@ -1,0 +1,116 @@
+#include "host_util.h"
+
+#include <string.h>
+
+namespace mv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return MV_E_CUDA;
+}
+
+int require_sm100() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = MV_E_CUDA;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev == cached_dev) return cached_rc;
+  int major = 0, minor = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cached_dev = dev;
+  if (major != 10) {
+    set_error("movii_b200 requires an sm_100 (B200) device; device %d is sm_%d%d — no fallback path exists",
+              dev, major, minor);
+    cached_rc = MV_E_ARCH;
+  } else {
+    cached_rc = MV_OK;
+  }
+  return cached_rc;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached > 0 ? cached : 148;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return MV_E_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return MV_E_SHAPE;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i];
+      if (strides_bytes[i] % 16 != 0) {
+        set_error("TMA stride %llu (dim %d) is not a multiple of 16 bytes",
+                  static_cast<unsigned long long>(strides_bytes[i]), i);
+        return MV_E_SHAPE;
+      }
+    }
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)",
+              static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]),
+              static_cast<unsigned long long>(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return MV_E_CUDA;
+  }
+  return MV_OK;
+}
+
+}  // namespace mv
+
+extern "C" const char* mv_last_error(void) { return mv::g_err; }
+extern "C" int mv_version(void) { return 100; }
+extern "C" int mv_device_check(void) { return mv::require_sm100(); }

@@ -1,0 +1,45 @@
+// Host-side helpers: thread-local error message, CUDA error mapping, TMA tensor-map encoding
+// (driver entry point fetched at run time so the library has no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/movii_b200.h"
+
+namespace mv {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+// MV_OK if the current device is CC 10.x; caches the answer per device.
+int require_sm100();
+int sm_count();
+
+// Encodes a tiled bf16 tensor map.  dims/strides innermost first; strides in BYTES for dims 1..rank-1
+// (dim 0 is contiguous).  Swizzle 128B requires box[0] * 2 bytes == 128.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+#define MV_CHECK_CUDA(expr)                                \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return mv::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define MV_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      mv::set_error(__VA_ARGS__);    \
+      return MV_E_SHAPE;             \
+    }                                \
+  } while (0)
+
+#define MV_CHECK_LAUNCH(name)                                    \
+  do {                                                           \
+    cudaError_t _e = cudaGetLastError();                         \
+    if (_e != cudaSuccess) return mv::cuda_fail(_e, name);       \
+  } while (0)
+
+}  // namespace mv

@@ -1,0 +1,181 @@
+"""ctypes binding of libmovii_b200.so (include/movii_b200.h).
+
+PyTorch here is plumbing only: it owns device memory and streams; every operator below is a
+hand-written sm_100a kernel reached through the C ABI.  There is no fallback: if the library is
+missing or the device is not a B200 the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "..", "lib", "libmovii_b200.so")
+
+MV_EPI_BF16 = 0
+MV_EPI_BF16_GELU = 1
+MV_EPI_RESID_F32 = 2
+MV_EPI_F32_ROUND = 3
+
+_lib = None
+_c = ctypes
+_i64 = _c.c_int64
+_int = _c.c_int
+_f32 = _c.c_float
+_ptr = _c.c_void_p
+
+# name -> argtypes (restype is always int); mirrors include/movii_b200.h one to one
+_SIGNATURES = {
+    "mv_gemm_bf16": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int, _int, _int, _int, _ptr],
+    "mv_attention_fwd": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr],
+    "mv_ln_modulate": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _f32, _int, _ptr],
+    "mv_rmsnorm_rope": [_ptr, _i64, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
+    "mv_patchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
+    "mv_head_unpatchify": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
+                           _f32, _ptr],
+    "mv_linear_f32_vec": [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _ptr],
+    "mv_sinusoid_embed": [_ptr, _int, _ptr, _int, _ptr],
+}
+EXPORTED_SYMBOLS = ["mv_last_error", "mv_version", "mv_device_check"] + sorted(_SIGNATURES)
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built — no fallback."""
+    global _lib
+    if _lib is None:
+        path = os.path.abspath(LIB_PATH)
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "libmovii_b200.so not found at %s — run `python moviigen1.1_b200/build.py` "
+                "(there is no non-CUDA fallback)" % path)
+        _lib = ctypes.CDLL(path)
+        _lib.mv_last_error.restype = ctypes.c_char_p
+        _lib.mv_version.restype = _int
+        _lib.mv_device_check.restype = _int
+        for name, args in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = args
+            fn.restype = _int
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().mv_last_error().decode()))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (movii_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def device_check():
+    _check(lib().mv_device_check(), "mv_device_check")
+
+
+def gemm(a, w, bias, out, epilogue, gate=None):
+    """out = epilogue(a @ w.T + bias).  a [M,K] bf16 (row stride any multiple of 8), w [N,K] bf16."""
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.float32, "bias")
+    _req(gate, torch.float32, "gate")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+    want = torch.float32 if epilogue in (MV_EPI_RESID_F32, MV_EPI_F32_ROUND) else torch.bfloat16
+    _req(out, want, "out")
+    _check(lib().mv_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
+                              M, N, K, epilogue, _stream()), "mv_gemm_bf16")
+    return out
+
+
+def attention(q, k, v, out, softmax_scale=None):
+    """q [Lq,H,128], k/v [Lk,H,128] bf16 views (last two dims contiguous), out [Lq,H,128] bf16."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+        assert t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1 and t.stride(1) == 128, n
+    Lq, H, _ = q.shape
+    Lk = k.shape[0]
+    assert v.shape[0] == Lk and k.shape[1] == H and v.shape[1] == H and out.shape[0] == Lq
+    if softmax_scale is None:
+        softmax_scale = 128 ** -0.5
+    _check(lib().mv_attention_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                  Lq, Lk, H, float(softmax_scale), _stream()), "mv_attention_fwd")
+    return out
+
+
+def ln_modulate(x, out, shift=None, scale=None, weight=None, bias=None, eps=1e-6, round_ln=False):
+    _req(x, torch.float32, "x"); _req(out, torch.bfloat16, "out")
+    for t, n in ((shift, "shift"), (scale, "scale"), (weight, "weight"), (bias, "bias")):
+        _req(t, torch.float32, n)
+        assert t is None or t.is_contiguous()
+    assert x.dim() == 2 and x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
+    M, C = x.shape
+    _check(lib().mv_ln_modulate(_p(x), x.stride(0), _p(shift), _p(scale), _p(weight), _p(bias), _p(out),
+                                out.stride(0), M, C, float(eps), int(round_ln), _stream()), "mv_ln_modulate")
+    return out
+
+
+def rmsnorm_rope(x, weight, cs=None, head_dim=128, eps=1e-6):
+    """In place on x [M,C] bf16 (row stride multiple of 8).  cs: [M, head_dim/2, 2] fp32 or None."""
+    _req(x, torch.bfloat16, "x"); _req(weight, torch.float32, "weight"); _req(cs, torch.float32, "cs")
+    assert x.dim() == 2 and x.stride(1) == 1 and weight.is_contiguous()
+    M, C = x.shape
+    if cs is not None:
+        assert cs.is_contiguous() and cs.shape == (M, head_dim // 2, 2), (cs.shape, M, head_dim)
+    _check(lib().mv_rmsnorm_rope(_p(x), x.stride(0), _p(weight), _p(cs), M, C, head_dim, float(eps), _stream()),
+           "mv_rmsnorm_rope")
+    return x
+
+
+def patchify(latent, out, patch_hw=(2, 2)):
+    _req(latent, torch.float32, "latent"); _req(out, torch.bfloat16, "out")
+    assert latent.is_contiguous() and out.is_contiguous() and latent.dim() == 4
+    C, F, H, W = latent.shape
+    ph, pw = patch_hw
+    assert out.shape == (F * (H // ph) * (W // pw), C * ph * pw)
+    _check(lib().mv_patchify(_p(latent), _p(out), C, F, H, W, ph, pw, _stream()), "mv_patchify")
+    return out
+
+
+def head_unpatchify(x, shift, scale, w, b, out, grid, patch_hw=(2, 2), eps=1e-6):
+    """x [>=L, C] fp32; w [ph*pw*Cout, C] fp32; out [Cout, F, Hp*ph, Wp*pw] fp32."""
+    for t, n in ((x, "x"), (shift, "shift"), (scale, "scale"), (w, "w"), (b, "b"), (out, "out")):
+        _req(t, torch.float32, n)
+    F, Hp, Wp = grid
+    ph, pw = patch_hw
+    C = x.shape[1]
+    Cout = out.shape[0]
+    assert w.is_contiguous() and w.shape == (ph * pw * Cout, C) and out.is_contiguous()
+    assert out.shape == (Cout, F, Hp * ph, Wp * pw) and x.shape[0] >= F * Hp * Wp and x.stride(1) == 1
+    _check(lib().mv_head_unpatchify(_p(x), x.stride(0), _p(shift), _p(scale), _p(w), _p(b), _p(out), F, Hp, Wp, ph,
+                                    pw, Cout, C, float(eps), _stream()), "mv_head_unpatchify")
+    return out
+
+
+def linear_f32_vec(x, w, b, out, act_in=0):
+    for t, n in ((x, "x"), (w, "w"), (b, "b"), (out, "out")):
+        _req(t, torch.float32, n)
+    N, K = w.shape
+    assert w.is_contiguous() and x.numel() == K and out.numel() == N
+    _check(lib().mv_linear_f32_vec(_p(x), _p(w), _p(b), _p(out), N, K, int(act_in), _stream()), "mv_linear_f32_vec")
+    return out
+
+
+def sinusoid_embed(t, out):
+    _req(out, torch.float32, "out")
+    assert t.is_cuda and t.numel() == 1 and t.dtype in (torch.int64, torch.float32)
+    _check(lib().mv_sinusoid_embed(_p(t), int(t.dtype == torch.int64), _p(out), out.numel(), _stream()),
+           "mv_sinusoid_embed")
+    return out

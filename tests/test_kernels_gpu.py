@@ -1,0 +1,203 @@
+"""-m gpu parity tests of the individual sm_100a kernels, called through the C ABI, against the CPU oracle
+(oracle/dit_oracle.py with bf16 cast points).  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+
+from oracle import dit_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (300, 256, 192), (64, 128, 64),
+                                   (1000, 5120, 5120), (512, 1280, 4096), (4096, 768, 1536)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm(mv, M, N, K, epi):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + epi)
+    a = (torch.randn(M, K, generator=g)).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, generator=g)
+    y = O.bf16_rt(a.float() @ w.float().t() + bias)
+    if epi == 0:
+        ref = y
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi)
+    elif epi == 1:
+        ref = O.bf16_rt(O.gelu_tanh(y))
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi)
+    elif epi == 2:
+        x0 = torch.randn(M, N, generator=g)
+        gate = torch.randn(N, generator=g)
+        ref = x0 + y * gate
+        out = x0.to(DEV)
+        mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi, gate=gate.to(DEV))
+    else:
+        ref = y
+        out = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+        mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi)
+    torch.cuda.synchronize()
+    # bf16 output rounding (2^-8 relative) is the only legitimate difference: fp32 accumulation order can flip
+    # a rounding, so compare in rel-L2 (<= 3e-3) and bound the worst element by 2 bf16 ulps.
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) <= 3e-3
+    err = (out.float().cpu() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2 * (1 if epi != 2 else 1 + gate.abs().max().item())
+    assert (err <= tol).all(), err.max().item()
+
+
+def test_gemm_no_bias_no_gate_strided(mv):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 200, 384, 256
+    big_a = torch.randn(M, K + 64, generator=g).bfloat16().to(DEV)
+    a = big_a[:, 32:32 + K]  # row stride K+64, offset 32 elements (64 B aligned)
+    w = (torch.randn(N, K, generator=g) / 16).bfloat16().to(DEV)
+    big_out = torch.zeros(M, N + 128, dtype=torch.float32, device=DEV)
+    out = big_out[:, 64:64 + N]
+    x0 = torch.randn(M, N, generator=g).to(DEV)
+    out.copy_(x0)
+    mv.gemm(a, w, None, out, 2)
+    ref = x0.cpu() + O.bf16_rt(a.float().cpu() @ w.float().cpu().t())
+    assert rel_l2(out, ref) <= 3e-3
+    assert (big_out[:, :64] == 0).all() and (big_out[:, 64 + N:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("Lq,Lk,H", [(256, 128, 1), (256, 256, 2), (300, 333, 2), (128, 512, 3), (1000, 512, 2),
+                                     (2048, 2048, 4), (4100, 4100, 1)])
+def test_attention(mv, Lq, Lk, H):
+    g = torch.Generator().manual_seed(Lq + 3 * Lk + H)
+    q = torch.randn(Lq, H, 128, generator=g).bfloat16()
+    k = torch.randn(Lk, H, 128, generator=g).bfloat16()
+    v = torch.randn(Lk, H, 128, generator=g).bfloat16()
+    ref = O.attention(q, k, v, O.bf16_rt)
+    out = torch.full((Lq, H, 128), float("nan"), dtype=torch.bfloat16, device=DEV)
+    mv.attention(q.to(DEV), k.to(DEV), v.to(DEV), out)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    # P is rounded to bf16 before P.V (as in flash-attn): rel-L2 <= 3e-3 of the fp32-softmax oracle... measured
+    # against bf16 outputs, so allow 5e-3; max-abs bounded by 2e-2 for unit-variance V.
+    assert rel_l2(out.float(), ref) <= 5e-3
+    assert (out.float().cpu() - ref).abs().max().item() <= 2e-2
+
+
+def test_attention_strided_views_and_scale(mv):
+    """q/k/v as column slices of one fused [L, 3*H*128] QKV buffer (how the DiT block calls it), sharp softmax."""
+    g = torch.Generator().manual_seed(11)
+    L, H = 640, 2
+    qkv = (torch.randn(L, 3 * H * 128, generator=g) * 2.0).bfloat16().to(DEV)
+    q = qkv[:, : H * 128].view(L, H, 128)[:, :, :]
+    q = qkv.as_strided((L, H, 128), (3 * H * 128, 128, 1), 0)
+    k = qkv.as_strided((L, H, 128), (3 * H * 128, 128, 1), H * 128)
+    v = qkv.as_strided((L, H, 128), (3 * H * 128, 128, 1), 2 * H * 128)
+    out = torch.empty(L, H, 128, dtype=torch.bfloat16, device=DEV)
+    mv.attention(q, k, v, out, softmax_scale=0.5)
+    ref = O.attention(q.cpu(), k.cpu(), v.cpu(), O.bf16_rt, scale=0.5)
+    assert rel_l2(out.float(), ref) <= 5e-3
+
+
+# ---------------------------------------------------------------------------------------------- rowops
+@pytest.mark.parametrize("M,C", [(7, 128), (33, 5120), (5, 1536)])
+@pytest.mark.parametrize("variant", ["plain", "mod", "affine", "round_mod"])
+def test_ln_modulate(mv, M, C, variant):
+    g = torch.Generator().manual_seed(M + C)
+    x = torch.randn(M, C, generator=g) * 3 + 0.5
+    shift = scale = w = b = None
+    if "mod" in variant:
+        shift, scale = torch.randn(C, generator=g), torch.randn(C, generator=g) * 0.3
+    if variant == "affine":
+        w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    h = O.layer_norm(x, 1e-6, w, b)
+    if variant == "round_mod":
+        h = O.bf16_rt(h)
+    if shift is not None:
+        h = h * (1 + scale) + shift
+    ref = O.bf16_rt(h)
+    out = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    mv.ln_modulate(x.to(DEV), out, None if shift is None else shift.to(DEV), None if scale is None else scale.to(DEV),
+                   None if w is None else w.to(DEV), None if b is None else b.to(DEV), 1e-6,
+                   variant == "round_mod")
+    assert rel_l2(out.float(), ref) <= 3e-3
+    assert (out.float().cpu() - ref).abs().max() <= 2.0 ** -6 * ref.abs().max()
+
+
+@pytest.mark.parametrize("M,C,hd,rope", [(9, 256, 128, True), (40, 5120, 128, True), (17, 5120, 128, False),
+                                         (6, 128, 32, True)])
+def test_rmsnorm_rope(mv, M, C, hd, rope):
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C + 64, generator=g) * 2).bfloat16()
+    wt = torch.randn(C, generator=g)
+    grid = (1, 1, M)
+    ang = O.rope_table((M, 1, 1), hd, M + 2)[:M] if rope else None
+    y = O.rms_norm(x[:, 8:8 + C], wt, 1e-6, O.bf16_rt)
+    if rope:
+        y = O.rope_apply(y.view(M, C // hd, hd), ang).reshape(M, C)
+    ref = O.bf16_rt(y)
+    xd = x.to(DEV)
+    cs = None
+    if rope:
+        cs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(DEV)
+    mv.rmsnorm_rope(xd[:, 8:8 + C], wt.to(DEV), cs, hd, 1e-6)
+    assert rel_l2(xd[:, 8:8 + C].float(), ref) <= 3e-3
+    assert torch.equal(xd[:, :8].cpu(), x[:, :8]) and torch.equal(xd[:, 8 + C:].cpu(), x[:, 8 + C:])
+
+
+def test_patchify(mv):
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(16, 3, 8, 12, generator=g)
+    ref, grid = O.patchify(lat, (1, 2, 2))
+    out = torch.empty(ref.shape, dtype=torch.bfloat16, device=DEV)
+    mv.patchify(lat.to(DEV), out)
+    assert torch.equal(out.float().cpu(), O.bf16_rt(ref))
+
+
+@pytest.mark.parametrize("grid,C", [((2, 3, 5), 256), ((3, 8, 8), 5120)])
+def test_head_unpatchify(mv, grid, C):
+    g = torch.Generator().manual_seed(C)
+    L = grid[0] * grid[1] * grid[2]
+    x = torch.randn(L + 5, C, generator=g) * 2
+    shift, scale = torch.randn(C, generator=g), torch.randn(C, generator=g) * 0.2
+    w, b = torch.randn(64, C, generator=g) / math.sqrt(C), torch.randn(64, generator=g)
+    h = O.layer_norm(x, 1e-6) * (1 + scale) + shift
+    ref = O.unpatchify(h.double() @ w.double().t() + b.double(), grid, (1, 2, 2), 16).float()
+    out = torch.empty(ref.shape, dtype=torch.float32, device=DEV)
+    mv.head_unpatchify(x.to(DEV), shift.to(DEV), scale.to(DEV), w.to(DEV), b.to(DEV), out, grid)
+    # fp32 end to end: 1e-5 relative
+    assert rel_l2(out, ref) <= 1e-5
+
+
+def test_time_embedding_path(mv):
+    g = torch.Generator().manual_seed(9)
+    dim, fd = 512, 256
+    t = torch.tensor([937], dtype=torch.int64)
+    sin_ref = O.sinusoidal_embedding_1d(fd, t).float()[0]
+    sin = torch.empty(fd, dtype=torch.float32, device=DEV)
+    mv.sinusoid_embed(t.to(DEV), sin)
+    assert (sin.cpu() - sin_ref).abs().max() <= 1e-6
+    w0, b0 = torch.randn(dim, fd, generator=g) * 0.05, torch.randn(dim, generator=g)
+    w1, b1 = torch.randn(dim * 6, dim, generator=g) * 0.05, torch.randn(dim * 6, generator=g)
+    e = torch.empty(dim, dtype=torch.float32, device=DEV)
+    e0 = torch.empty(dim * 6, dtype=torch.float32, device=DEV)
+    mv.linear_f32_vec(sin, w0.to(DEV), b0.to(DEV), e, act_in=0)
+    mv.linear_f32_vec(e, w1.to(DEV), b1.to(DEV), e0, act_in=1)
+    e_ref = sin_ref.double() @ w0.double().t() + b0.double()
+    e0_ref = torch.nn.functional.silu(e_ref) @ w1.double().t() + b1.double()
+    assert rel_l2(e, e_ref) <= 1e-5 and rel_l2(e0, e0_ref) <= 1e-5
+
+
+def test_errors_are_reported(mv):
+    a = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)   # K=12 not a multiple of 8
+    w = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)
+    out = torch.zeros(8, 8, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        mv.gemm(a, w, None, out, 0)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        mv.gemm(a.cpu(), w, None, out, 0)

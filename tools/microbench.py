@@ -1,0 +1,100 @@
+"""Kernel micro-benchmarks on one B200 (CUDA events, L2 flushed between iterations).
+Prints one JSON line per case; used to fill profiles/ and DESIGN.md.  Not the headline bench (bench.py)."""
+import json
+import math
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "moviigen1.1_b200"))
+import movii_b200 as mv  # noqa: E402
+
+DEV = "cuda"
+FLUSH = None
+
+
+def timeit(fn, iters=5, warmup=2):
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        FLUSH.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def bench_gemm(M, N, K, epi=0):
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    f32 = epi in (2, 3)
+    out = torch.zeros(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=DEV)
+    ms = timeit(lambda: mv.gemm(a, w, bias, out, epi))
+    ms_ref = timeit(lambda: torch.nn.functional.linear(a, w, bias.bfloat16()))
+    fl = 2.0 * M * N * K
+    print(json.dumps(dict(kind="gemm", M=M, N=N, K=K, epi=epi, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+                          cublas_ms=round(ms_ref, 4), cublas_tflops=round(fl / ms_ref / 1e9, 1))), flush=True)
+
+
+def bench_attn(L, H, Lk=None):
+    Lk = Lk or L
+    q = torch.randn(L, H, 128, device=DEV).bfloat16()
+    k = torch.randn(Lk, H, 128, device=DEV).bfloat16()
+    v = torch.randn(Lk, H, 128, device=DEV).bfloat16()
+    o = torch.empty_like(q)
+    ms = timeit(lambda: mv.attention(q, k, v, o), iters=3, warmup=1)
+    fl = 4.0 * L * Lk * H * 128
+    rec = dict(kind="attn", Lq=L, Lk=Lk, H=H, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))
+    try:
+        from flash_attn import flash_attn_func
+        ms_fa = timeit(lambda: flash_attn_func(q[None], k[None], v[None]), iters=3, warmup=1)
+        rec.update(fa2_ms=round(ms_fa, 4), fa2_tflops=round(fl / ms_fa / 1e9, 1))
+        ref = flash_attn_func(q[None], k[None], v[None])[0]
+        rec["max_abs_vs_fa2"] = round((ref.float() - o.float()).abs().max().item(), 5)
+    except Exception as ex:  # flash-attn absent or not runnable on this box
+        rec["fa2_error"] = repr(ex)[:120]
+    print(json.dumps(rec), flush=True)
+
+
+def bench_rowops(M=75600, C=5120):
+    x = torch.randn(M, C, device=DEV)
+    out = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    sh, sc = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    ms = timeit(lambda: mv.ln_modulate(x, out, sh, sc))
+    gb = M * C * 6 / 1e9
+    print(json.dumps(dict(kind="ln_modulate", M=M, C=C, ms=round(ms, 4), gbs=round(gb / ms * 1e3, 1))), flush=True)
+    qk = torch.randn(M, C, device=DEV).bfloat16()
+    wt = torch.randn(C, device=DEV)
+    cs = torch.randn(M, 64, 2, device=DEV)
+    ms = timeit(lambda: mv.rmsnorm_rope(qk, wt, cs))
+    gb = (M * C * 4 + M * 512) / 1e9
+    print(json.dumps(dict(kind="rmsnorm_rope", M=M, C=C, ms=round(ms, 4), gbs=round(gb / ms * 1e3, 1))), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "attn", "rowops"]
+    mv.device_check()
+    if "gemm" in which:
+        for (M, N, K, epi) in [(8192, 8192, 8192, 0), (75600, 15360, 5120, 0), (75600, 5120, 5120, 2),
+                               (75600, 13824, 5120, 1), (75600, 5120, 13824, 2), (16380, 15360, 5120, 0),
+                               (512, 5120, 4096, 1)]:
+            bench_gemm(M, N, K, epi)
+    if "attn" in which:
+        for (L, H, Lk) in [(4096, 40, None), (16384, 40, None), (32768, 10, None), (75600, 5, None),
+                           (75600, 40, 512)]:
+            bench_attn(L, H, Lk)
+    if "rowops" in which:
+        bench_rowops()
