@@ -53,6 +53,14 @@ int mv_device_check(void);
 int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
                  int64_t ldo, const float* gate, int M, int N, int K, int epilogue, mv_stream_t stream);
 
+/* Same contraction with A stored as K/a_kblock slabs: A[m, j*a_kblock + c] = A_base[j*a_block_stride + m*lda + c].
+ * This is the layout the Ulysses attention-output all-to-all delivers ([src rank][local token][local heads*128],
+ * xdit_context_parallel.py:185-197), so the o projection consumes it without a transpose pass.
+ * a_kblock must be a multiple of 64. */
+int mv_gemm_bf16_ksplit(const void* A, int64_t lda, int64_t a_block_stride, int a_kblock, const void* W, int64_t ldw,
+                        const float* bias, void* out, int64_t ldo, const float* gate, int M, int N, int K,
+                        int epilogue, mv_stream_t stream);
+
 /* o[Lq,H,128] = softmax(q k^T * scale) v, non-causal, bf16 in/out, fp32 softmax and accumulation;
  * q,k,v,o are [L, H, 128] views with row strides ldq/ldk/ldv/ldo (elements) and heads contiguous
  * (head h at column offset h*128).  Keys/values are rows [0, Lk).  Replaces
@@ -79,6 +87,12 @@ int mv_ln_modulate(const float* x, int64_t ldx, const float* shift, const float*
 int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, const float* cs, int M, int C,
                     int head_dim, float eps, mv_stream_t stream);
 
+/* mv_rmsnorm_rope with the Ulysses head scatter fused in (xdit_context_parallel.py:169-190): when out != NULL the
+ * result goes to out[dst][row][C/sp_world] (dst = destination rank of the head group), the all-to-all send
+ * layout, instead of in place; weight == NULL skips the norm (plain scatter of V); cs == NULL skips RoPE. */
+int mv_qkv_prepare(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16, int sp_world,
+                   int M, int C, int head_dim, float eps, mv_stream_t stream);
+
 /* A_bf16[L, C*ph*pw] <- latent fp32 [C, F, H, W], patch (1,ph,pw); column = c*ph*pw + i*pw + j, the
  * flatten(1) order of patch_embedding.weight (model.py:445-450,529-533). */
 int mv_patchify(const float* latent, void* a_bf16, int C, int F, int H, int W, int ph, int pw,
@@ -90,6 +104,14 @@ int mv_patchify(const float* latent, void* a_bf16, int C, int F, int H, int W, i
 int mv_head_unpatchify(const float* x, int64_t ldx, const float* shift, const float* scale, const float* Wh,
                        const float* bh, float* out, int F, int Hp, int Wp, int ph, int pw, int Cout, int C,
                        float eps, mv_stream_t stream);
+
+/* Head only, token-major: out_tokens[L, nout] (fp32) — the sequence-parallel path all-gathers these rows
+ * (xdit_context_parallel.py:145-148) and then calls mv_unpatchify. */
+int mv_head_tokens(const float* x, int64_t ldx, const float* shift, const float* scale, const float* Wh,
+                   const float* bh, float* out_tokens, int L, int nout, int C, float eps, mv_stream_t stream);
+/* tokens[L, ph*pw*Cout] -> out[Cout, F, Hp*ph, Wp*pw] (model.py:581-609). */
+int mv_unpatchify(const float* tokens, float* out, int F, int Hp, int Wp, int ph, int pw, int Cout,
+                  mv_stream_t stream);
 
 /* out[N] = W[N,K] . act(x[K]) + b[N], fp32 (M = 1).  act_in: 0 none, 1 SiLU.  Replaces the fp32
  * time_embedding / time_projection Linears (model.py:455-457,541-545). */

@@ -33,6 +33,7 @@ struct GemmParams {
   int64_t ldo;
   int M, N, K;
   int num_m, num_n, num_tiles, num_kb;
+  int a_kblock;  // > 0: A is split along K into blocks of a_kblock columns (3-D tensor map {k, m, block})
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
@@ -93,7 +94,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kStageBytes);
-          tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * BK, m_blk * BM);
+          if (p.a_kblock > 0) {
+            const int k0 = kb * BK;
+            const int blk = k0 / p.a_kblock;
+            tma_load_3d(sA + stage * kABytes, &tmA, &full[stage], k0 - blk * p.a_kblock, m_blk * BM, blk);
+          } else {
+            tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * BK, m_blk * BM);
+          }
           tma_load_2d(sB + stage * kBBytes, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == kStages) {
             stage = 0;
@@ -252,28 +259,36 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 }  // namespace mv
 
-extern "C" int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
-                            int64_t ldo, const float* gate, int M, int N, int K, int epilogue,
-                            mv_stream_t stream) {
+static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_kblock, const void* W, int64_t ldw,
+                     const float* bias, void* out, int64_t ldo, const float* gate, int M, int N, int K, int epilogue,
+                     mv_stream_t stream) {
   using namespace mv;
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(M > 0 && N > 0 && K > 0, "mv_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   MV_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "mv_gemm_bf16: K/lda/ldw must be multiples of 8 (K=%d lda=%lld ldw=%lld)",
              K, (long long)lda, (long long)ldw);
-  MV_REQUIRE(lda >= K && ldw >= K && ldo >= N, "mv_gemm_bf16: leading dimensions too small");
+  MV_REQUIRE(lda >= (a_kblock > 0 ? a_kblock : K) && ldw >= K && ldo >= N, "mv_gemm_bf16: leading dimensions too small");
   MV_REQUIRE(epilogue >= 0 && epilogue <= 3, "mv_gemm_bf16: unknown epilogue %d", epilogue);
   const bool f32_out = (epilogue == MV_EPI_RESID_F32 || epilogue == MV_EPI_F32_ROUND);
   MV_REQUIRE(ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "mv_gemm_bf16: output must be 16-byte aligned with 16-byte aligned rows");
   MV_REQUIRE(gate == nullptr || (reinterpret_cast<uintptr_t>(gate) & 15) == 0, "mv_gemm_bf16: gate must be 16B aligned");
+  MV_REQUIRE(a_kblock == 0 || (a_kblock % BK == 0 && K % a_kblock == 0 && a_block_stride % 8 == 0),
+             "mv_gemm_bf16_ksplit: k block %d must be a multiple of %d dividing K=%d", a_kblock, BK, K);
 
   CUtensorMap tmA, tmB;
-  {
+  if (a_kblock == 0) {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     uint64_t str[2] = {2, static_cast<uint64_t>(lda) * 2};
     uint32_t box[2] = {BK, BM};
     rc = make_tmap_bf16(&tmA, A, 2, dims, str, box, true);
+    if (rc != MV_OK) return rc;
+  } else {
+    uint64_t dims[3] = {static_cast<uint64_t>(a_kblock), static_cast<uint64_t>(M), static_cast<uint64_t>(K / a_kblock)};
+    uint64_t str[3] = {2, static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(a_block_stride) * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    rc = make_tmap_bf16(&tmA, A, 3, dims, str, box, true);
     if (rc != MV_OK) return rc;
   }
   {
@@ -295,6 +310,7 @@ extern "C" int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.num_n = (N + BN - 1) / BN;
   p.num_tiles = p.num_m * p.num_n;
   p.num_kb = (K + BK - 1) / BK;
+  p.a_kblock = a_kblock;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
     case MV_EPI_BF16: return launch_gemm<MV_EPI_BF16>(tmA, tmB, p, st);
@@ -302,4 +318,16 @@ extern "C" int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     case MV_EPI_RESID_F32: return launch_gemm<MV_EPI_RESID_F32>(tmA, tmB, p, st);
     default: return launch_gemm<MV_EPI_F32_ROUND>(tmA, tmB, p, st);
   }
+}
+
+extern "C" int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                            int64_t ldo, const float* gate, int M, int N, int K, int epilogue,
+                            mv_stream_t stream) {
+  return gemm_impl(A, lda, 0, 0, W, ldw, bias, out, ldo, gate, M, N, K, epilogue, stream);
+}
+
+extern "C" int mv_gemm_bf16_ksplit(const void* A, int64_t lda, int64_t a_block_stride, int a_kblock, const void* W,
+                                   int64_t ldw, const float* bias, void* out, int64_t ldo, const float* gate, int M,
+                                   int N, int K, int epilogue, mv_stream_t stream) {
+  return gemm_impl(A, lda, a_block_stride, a_kblock, W, ldw, bias, out, ldo, gate, M, N, K, epilogue, stream);
 }

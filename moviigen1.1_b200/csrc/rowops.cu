@@ -96,9 +96,14 @@ ln_modulate_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
 // --------------------------------------------------------------------------------------------
 constexpr int kRmsVec = 4;  // uint4 per thread -> C <= 256*8*4 = 8192
 
+// When `out` is given the result is written out of place in the Ulysses send layout
+// out[dst][row][c'] with dst = col / (C / sp_world), c' = col % (C / sp_world) (rows = gridDim.x), i.e. the
+// head-scatter of xdit_context_parallel.py:185-190 is fused into this pass.  weight == nullptr skips the
+// norm (plain scatter copy, used for V).
 __global__ void __launch_bounds__(kRowThreads)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ weight,
-                    const float* __restrict__ cs, int C, int head_dim, float eps) {
+                    const float* __restrict__ cs, int C, int head_dim, float eps,
+                    __nv_bfloat16* __restrict__ out, int sp_world) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
@@ -118,8 +123,10 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __re
       }
     }
   }
-  const float rinv = rsqrtf(block_sum(ss, red) / static_cast<float>(C) + eps);
+  const float rinv = weight != nullptr ? rsqrtf(block_sum(ss, red) / static_cast<float>(C) + eps) : 1.f;
   const int half = head_dim >> 1;
+  const int cols_per_rank = C / sp_world;
+  const int rows_total = gridDim.x;
   const float* csr = cs != nullptr ? cs + static_cast<int64_t>(row) * head_dim : nullptr;  // [half][2]
 #pragma unroll
   for (int i = 0; i < kRmsVec; ++i) {
@@ -127,6 +134,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __re
     if (idx < nvec) {
       const int col = idx << 3;
       uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      if (weight != nullptr) {
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col) + 1);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -145,8 +153,15 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __re
         }
         u[k] = pack_bf16(a, bb);
       }
+      }
       (void)half;
-      xr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
+      if (out == nullptr) {
+        xr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
+      } else {
+        const int dst = col / cols_per_rank, cc = col - dst * cols_per_rank;
+        uint4* o = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(dst) * rows_total + row) * cols_per_rank + cc);
+        *o = make_uint4(u[0], u[1], u[2], u[3]);
+      }
     }
   }
 }
@@ -251,6 +266,17 @@ head_unpatchify_kernel(const float* __restrict__ x, int64_t ldx, const float* __
     __syncthreads();
   }
   const int Ho = Hp * ph, Wo = Wp * pw;
+  if (F == 0) {  // token-major output [L, nout] (sequence-parallel path: all_gather then mv_unpatchify)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = row0 + tr + rr;
+      if (row >= L) continue;
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+        if (tn + n < nout) out[static_cast<int64_t>(row) * nout + tn + n] = acc[rr][n] + bh[tn + n];
+    }
+    return;
+  }
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int row = row0 + tr + rr;
@@ -265,6 +291,25 @@ head_unpatchify_kernel(const float* __restrict__ x, int64_t ldx, const float* __
       const int i = o / (Cout * pw);
       out[((static_cast<int64_t>(c) * F + f) * Ho + (hq * ph + i)) * Wo + (wq * pw + j)] = acc[rr][n] + bh[o];
     }
+  }
+}
+
+// tokens [L, ph*pw*Cout] -> video [Cout, F, Hp*ph, Wp*pw]                       model.py:581-609
+__global__ void unpatchify_kernel(const float* __restrict__ tok, float* __restrict__ out, int F, int Hp, int Wp,
+                                  int ph, int pw, int Cout) {
+  const int nout = ph * pw * Cout;
+  const int64_t total = static_cast<int64_t>(F) * Hp * Wp * nout;
+  const int Ho = Hp * ph, Wo = Wp * pw;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // iterate in OUTPUT order so that stores coalesce: t = ((c*F + f)*Ho + y)*Wo + x
+    const int x = static_cast<int>(t % Wo);
+    const int y = static_cast<int>((t / Wo) % Ho);
+    const int f = static_cast<int>((t / (static_cast<int64_t>(Wo) * Ho)) % F);
+    const int c = static_cast<int>(t / (static_cast<int64_t>(Wo) * Ho * F));
+    const int wq = x / pw, j = x % pw, hq = y / ph, i = y % ph;
+    const int64_t row = (static_cast<int64_t>(f) * Hp + hq) * Wp + wq;
+    out[t] = tok[row * nout + (i * pw + j) * Cout + c];
   }
 }
 
@@ -337,15 +382,25 @@ extern "C" int mv_ln_modulate(const float* x, int64_t ldx, const float* shift, c
 
 extern "C" int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, const float* cs, int M, int C,
                                int head_dim, float eps, mv_stream_t stream) {
+  return mv_qkv_prepare(x_bf16, ld, weight, cs, nullptr, 1, M, C, head_dim, eps, stream);
+}
+
+extern "C" int mv_qkv_prepare(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16,
+                              int sp_world, int M, int C, int head_dim, float eps, mv_stream_t stream) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(M > 0 && C > 0, "mv_rmsnorm_rope: empty problem");
+  MV_REQUIRE(sp_world >= 1 && C % sp_world == 0 && (C / sp_world) % head_dim == 0,
+             "mv_qkv_prepare: C=%d is not divisible into %d head groups", C, sp_world);
+  MV_REQUIRE(out_bf16 != nullptr || sp_world == 1, "mv_qkv_prepare: scatter needs an output buffer");
+  MV_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "mv_qkv_prepare: out must be 16B aligned");
   MV_REQUIRE(C % 8 == 0 && C <= kRowThreads * 8 * kRmsVec, "mv_rmsnorm_rope: C=%d must be a multiple of 8 and <= %d", C,
              kRowThreads * 8 * kRmsVec);
   MV_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "mv_rmsnorm_rope: rows must be 16B aligned");
   MV_REQUIRE(head_dim > 0 && head_dim % 2 == 0 && C % head_dim == 0, "mv_rmsnorm_rope: bad head_dim %d", head_dim);
   rmsnorm_rope_kernel<<<M, kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(x_bf16), ld, weight, cs, C, head_dim, eps);
+      reinterpret_cast<__nv_bfloat16*>(x_bf16), ld, weight, cs, C, head_dim, eps,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), sp_world);
   MV_CHECK_LAUNCH("rmsnorm_rope_kernel");
   return MV_OK;
 }
@@ -402,5 +457,32 @@ extern "C" int mv_sinusoid_embed(const void* t, int t_is_int64, float* out, int 
   MV_REQUIRE(dim > 0 && dim % 2 == 0, "mv_sinusoid_embed: dim must be even");
   sinusoid_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, t_is_int64, out, dim);
   MV_CHECK_LAUNCH("sinusoid_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_head_tokens(const float* x, int64_t ldx, const float* shift, const float* scale, const float* Wh,
+                              const float* bh, float* out_tokens, int L, int nout, int C, float eps,
+                              mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(L > 0 && C > 0 && nout > 0 && nout <= kHeadNOut, "mv_head_tokens: bad shape L=%d nout=%d", L, nout);
+  const int blocks = (L + kHeadRows - 1) / kHeadRows;
+  // F = 0 selects the token-major store; (ph, pw, Cout) = (1, 1, nout)
+  head_unpatchify_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, shift, scale, Wh, bh,
+                                                                               out_tokens, L, 0, 1, 1, 1, 1, nout, C, eps);
+  MV_CHECK_LAUNCH("head_tokens_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_unpatchify(const float* tokens, float* out, int F, int Hp, int Wp, int ph, int pw, int Cout,
+                             mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(F > 0 && Hp > 0 && Wp > 0 && ph > 0 && pw > 0 && Cout > 0, "mv_unpatchify: bad shape");
+  const int64_t total = static_cast<int64_t>(F) * Hp * Wp * ph * pw * Cout;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  unpatchify_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, out, F, Hp, Wp, ph, pw, Cout);
+  MV_CHECK_LAUNCH("unpatchify_kernel");
   return MV_OK;
 }

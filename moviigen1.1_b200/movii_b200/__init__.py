@@ -30,6 +30,10 @@ _SIGNATURES = {
     "mv_attention_fwd": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr],
     "mv_ln_modulate": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _f32, _int, _ptr],
     "mv_rmsnorm_rope": [_ptr, _i64, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
+    "mv_gemm_bf16_ksplit": [_ptr, _i64, _i64, _int, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int, _int, _int, _int, _ptr],
+    "mv_qkv_prepare": [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _int, _int, _f32, _ptr],
+    "mv_head_tokens": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
+    "mv_unpatchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_patchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_head_unpatchify": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
                            _f32, _ptr],
@@ -64,6 +68,33 @@ def _check(rc, what):
         raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().mv_last_error().decode()))
 
 
+LAUNCHES = 0          # kernels launched through the C ABI by this process (bench.py reports it)
+_TIMED = {}           # entry point -> list of (start_event, end_event); filled while enabled via time_kernels()
+
+
+def time_kernels(names):
+    """Enable (list of entry-point names) or disable (None) per-launch CUDA-event timing on the launching stream."""
+    _TIMED.clear()
+    for n in names or ():
+        _TIMED[n] = []
+    return _TIMED
+
+
+def _call(name, *args):
+    global LAUNCHES
+    rec = _TIMED.get(name)
+    if rec is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib(), name)(*args)
+        e.record()
+        rec.append((s, e, args))
+    else:
+        rc = getattr(lib(), name)(*args)
+    LAUNCHES += 1
+    _check(rc, name)
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -95,8 +126,8 @@ def gemm(a, w, bias, out, epilogue, gate=None):
     assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
     want = torch.float32 if epilogue in (MV_EPI_RESID_F32, MV_EPI_F32_ROUND) else torch.bfloat16
     _req(out, want, "out")
-    _check(lib().mv_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
-                              M, N, K, epilogue, _stream()), "mv_gemm_bf16")
+    _call("mv_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
+                              M, N, K, epilogue, _stream())
     return out
 
 
@@ -110,8 +141,8 @@ def attention(q, k, v, out, softmax_scale=None):
     assert v.shape[0] == Lk and k.shape[1] == H and v.shape[1] == H and out.shape[0] == Lq
     if softmax_scale is None:
         softmax_scale = 128 ** -0.5
-    _check(lib().mv_attention_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
-                                  Lq, Lk, H, float(softmax_scale), _stream()), "mv_attention_fwd")
+    _call("mv_attention_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                  Lq, Lk, H, float(softmax_scale), _stream())
     return out
 
 
@@ -122,8 +153,8 @@ def ln_modulate(x, out, shift=None, scale=None, weight=None, bias=None, eps=1e-6
         assert t is None or t.is_contiguous()
     assert x.dim() == 2 and x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
     M, C = x.shape
-    _check(lib().mv_ln_modulate(_p(x), x.stride(0), _p(shift), _p(scale), _p(weight), _p(bias), _p(out),
-                                out.stride(0), M, C, float(eps), int(round_ln), _stream()), "mv_ln_modulate")
+    _call("mv_ln_modulate", _p(x), x.stride(0), _p(shift), _p(scale), _p(weight), _p(bias), _p(out),
+                                out.stride(0), M, C, float(eps), int(round_ln), _stream())
     return out
 
 
@@ -134,8 +165,7 @@ def rmsnorm_rope(x, weight, cs=None, head_dim=128, eps=1e-6):
     M, C = x.shape
     if cs is not None:
         assert cs.is_contiguous() and cs.shape == (M, head_dim // 2, 2), (cs.shape, M, head_dim)
-    _check(lib().mv_rmsnorm_rope(_p(x), x.stride(0), _p(weight), _p(cs), M, C, head_dim, float(eps), _stream()),
-           "mv_rmsnorm_rope")
+    _call("mv_rmsnorm_rope", _p(x), x.stride(0), _p(weight), _p(cs), M, C, head_dim, float(eps), _stream())
     return x
 
 
@@ -145,7 +175,7 @@ def patchify(latent, out, patch_hw=(2, 2)):
     C, F, H, W = latent.shape
     ph, pw = patch_hw
     assert out.shape == (F * (H // ph) * (W // pw), C * ph * pw)
-    _check(lib().mv_patchify(_p(latent), _p(out), C, F, H, W, ph, pw, _stream()), "mv_patchify")
+    _call("mv_patchify", _p(latent), _p(out), C, F, H, W, ph, pw, _stream())
     return out
 
 
@@ -159,8 +189,8 @@ def head_unpatchify(x, shift, scale, w, b, out, grid, patch_hw=(2, 2), eps=1e-6)
     Cout = out.shape[0]
     assert w.is_contiguous() and w.shape == (ph * pw * Cout, C) and out.is_contiguous()
     assert out.shape == (Cout, F, Hp * ph, Wp * pw) and x.shape[0] >= F * Hp * Wp and x.stride(1) == 1
-    _check(lib().mv_head_unpatchify(_p(x), x.stride(0), _p(shift), _p(scale), _p(w), _p(b), _p(out), F, Hp, Wp, ph,
-                                    pw, Cout, C, float(eps), _stream()), "mv_head_unpatchify")
+    _call("mv_head_unpatchify", _p(x), x.stride(0), _p(shift), _p(scale), _p(w), _p(b), _p(out), F, Hp, Wp, ph,
+                                    pw, Cout, C, float(eps), _stream())
     return out
 
 
@@ -169,13 +199,63 @@ def linear_f32_vec(x, w, b, out, act_in=0):
         _req(t, torch.float32, n)
     N, K = w.shape
     assert w.is_contiguous() and x.numel() == K and out.numel() == N
-    _check(lib().mv_linear_f32_vec(_p(x), _p(w), _p(b), _p(out), N, K, int(act_in), _stream()), "mv_linear_f32_vec")
+    _call("mv_linear_f32_vec", _p(x), _p(w), _p(b), _p(out), N, K, int(act_in), _stream())
     return out
 
 
 def sinusoid_embed(t, out):
     _req(out, torch.float32, "out")
     assert t.is_cuda and t.numel() == 1 and t.dtype in (torch.int64, torch.float32)
-    _check(lib().mv_sinusoid_embed(_p(t), int(t.dtype == torch.int64), _p(out), out.numel(), _stream()),
-           "mv_sinusoid_embed")
+    _call("mv_sinusoid_embed", _p(t), int(t.dtype == torch.int64), _p(out), out.numel(), _stream())
+    return out
+
+
+def gemm_ksplit(a_blocks, w, bias, out, epilogue, gate=None):
+    """Like gemm() with A given as [nblk, M, Kb] slabs (A[m, j*Kb + c] = a_blocks[j, m, c]); Kb % 64 == 0."""
+    _req(a_blocks, torch.bfloat16, "a_blocks"); _req(w, torch.bfloat16, "w"); _req(bias, torch.float32, "bias")
+    _req(gate, torch.float32, "gate")
+    assert a_blocks.dim() == 3 and a_blocks.stride(2) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    nblk, M, Kb = a_blocks.shape
+    N, K = w.shape
+    assert K == nblk * Kb and out.shape == (M, N)
+    want = torch.float32 if epilogue in (MV_EPI_RESID_F32, MV_EPI_F32_ROUND) else torch.bfloat16
+    _req(out, want, "out")
+    _call("mv_gemm_bf16_ksplit", _p(a_blocks), a_blocks.stride(1), a_blocks.stride(0), Kb, _p(w), w.stride(0),
+                                     _p(bias), _p(out), out.stride(0), _p(gate), M, N, K, epilogue, _stream())
+    return out
+
+
+def qkv_prepare(x, weight, cs, out, sp_world, head_dim=128, eps=1e-6):
+    """rmsnorm (if weight) + rope (if cs) of x [M,C] bf16, written head-scattered to out [sp_world, M, C/sp_world]."""
+    _req(x, torch.bfloat16, "x"); _req(weight, torch.float32, "weight"); _req(cs, torch.float32, "cs")
+    _req(out, torch.bfloat16, "out")
+    assert x.dim() == 2 and x.stride(1) == 1 and out.is_contiguous()
+    M, C = x.shape
+    assert out.numel() == M * C
+    if cs is not None:
+        assert cs.is_contiguous() and cs.shape == (M, head_dim // 2, 2)
+    _call("mv_qkv_prepare", _p(x), x.stride(0), _p(weight), _p(cs), _p(out), sp_world, M, C, head_dim, float(eps),
+                                _stream())
+    return out
+
+
+def head_tokens(x, shift, scale, w, b, out, eps=1e-6):
+    for t, n in ((x, "x"), (shift, "shift"), (scale, "scale"), (w, "w"), (b, "b"), (out, "out")):
+        _req(t, torch.float32, n)
+    L, C = x.shape
+    nout = w.shape[0]
+    assert w.is_contiguous() and out.is_contiguous() and out.shape == (L, nout) and x.stride(1) == 1
+    _call("mv_head_tokens", _p(x), x.stride(0), _p(shift), _p(scale), _p(w), _p(b), _p(out), L, nout, C,
+                                float(eps), _stream())
+    return out
+
+
+def unpatchify(tokens, out, grid, patch_hw=(2, 2)):
+    _req(tokens, torch.float32, "tokens"); _req(out, torch.float32, "out")
+    F, Hp, Wp = grid
+    ph, pw = patch_hw
+    Cout = out.shape[0]
+    assert tokens.is_contiguous() and out.is_contiguous() and out.shape == (Cout, F, Hp * ph, Wp * pw)
+    assert tokens.shape[0] >= F * Hp * Wp and tokens.shape[1] == ph * pw * Cout
+    _call("mv_unpatchify", _p(tokens), _p(out), F, Hp, Wp, ph, pw, Cout, _stream())
     return out

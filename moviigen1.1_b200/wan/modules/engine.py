@@ -109,25 +109,27 @@ def self_attention_core(ws, rows, kv_rows, num_heads):
     mv.attention(q, k, v, ws.attn[:rows].view(rows, num_heads, 128))
 
 
-def block_forward(bw, ws, rows, e, cs, ctx, kv_rows, first_block=False, attn_core=None):
+def block_forward(bw, ws, rows, e, cs, ctx, kv_rows, first_block=False, sp=None):
     """One WanAttentionBlock on ws.x[:rows] in place.  e: [6, C] fp32 = modulation + e0 (model.py:292-295);
     cs: RoPE table for these rows; ctx: [Lc, C] bf16 embedded text; kv_rows: keys of real tokens
-    (flash_attention(k_lens=seq_lens), model.py:146-151)."""
+    (flash_attention(k_lens=seq_lens), model.py:146-151).  sp: UlyssesGroup -> rows are this rank's token shard and
+    the attention core runs head-parallel after an all-to-all (xdit_context_parallel.py:155-198)."""
     C, nh, eps = bw.dim, bw.num_heads, bw.eps
     x, h, qkv, attn = ws.x[:rows], ws.h[:rows], ws.qkv[:rows], ws.attn[:rows]
+    if not bw.qk_norm:
+        raise NotImplementedError("qk_norm=False is not a configuration the 14B model uses")
     # --- self-attention: x += o(attn(rope(rms(q)), rope(rms(k)), v)) * e2          model.py:298-302
     mv.ln_modulate(x, h, shift=e[0], scale=e[1], eps=eps, round_ln=first_block)
     mv.gemm(h, bw.w_qkv, bw.b_qkv, qkv, mv.MV_EPI_BF16)
-    if bw.qk_norm:
+    if sp is None or sp.world == 1:
         mv.rmsnorm_rope(qkv[:, 0:C], bw.g_q, cs, 128, eps)
         mv.rmsnorm_rope(qkv[:, C:2 * C], bw.g_k, cs, 128, eps)
-    else:
-        raise NotImplementedError("qk_norm=False is not a configuration the 14B model uses")
-    if attn_core is None:
         self_attention_core(ws, rows, kv_rows, nh)
+        mv.gemm(attn, bw.w_o, bw.b_o, x, mv.MV_EPI_RESID_F32, gate=e[2])
     else:
-        attn_core(ws, rows)
-    mv.gemm(attn, bw.w_o, bw.b_o, x, mv.MV_EPI_RESID_F32, gate=e[2])
+        from ..distributed.ulysses import sp_self_attention
+        o_slabs = sp_self_attention(mv, sp, ws, rows, bw, cs, kv_rows)
+        mv.gemm_ksplit(o_slabs, bw.w_o, bw.b_o, x, mv.MV_EPI_RESID_F32, gate=e[2])
     # --- cross-attention: x += o(attn(rms(q(norm3 x)), rms(k(ctx)), v(ctx)))        model.py:306,159-181
     if bw.n3_w is not None:
         mv.ln_modulate(x, h, weight=bw.n3_w, bias=bw.n3_b, eps=eps)
@@ -280,4 +282,31 @@ class DitEngine:
         out = torch.empty(C_out, grid[0], grid[1] * self.patch[1], grid[2] * self.patch[2], dtype=F32,
                           device=self.device)
         self.head(ws, seq_len, e, grid, out)
+        return out
+
+    # -- WanModel.forward under Ulysses sequence parallelism (xdit_context_parallel.py:65-152) ---------
+    def forward_single_sp(self, latent, t, context, seq_len, freqs, grp):
+        from ..distributed.ulysses import token_range
+        start, rows = token_range(seq_len, grp.world, grp.rank)
+        ws = self.workspace(rows)
+        # only this rank's tokens are embedded (the reference embeds the full sequence on every rank and then
+        # chunks, :137-139 — same values, P times less work)
+        grid, L = self.embed_patches(latent, ws, start, rows)
+        if L > seq_len:
+            raise AssertionError("seq_len smaller than the token count")
+        e, e0 = self.embed_time(t)
+        ctx = self.embed_text(context)
+        cs = self.rope_table(freqs, grid, seq_len, start, rows)
+        E = self.mods + e0.unsqueeze(0)
+        for i, bw in enumerate(self.blocks):
+            # the reference USP path does not un-pad: all seq_len keys are attended (:178-183 TODO)
+            block_forward(bw, ws, rows, E[i], cs, ctx, seq_len, first_block=(i == 0), sp=grp)
+        em = self.head_mod + e.view(1, -1)
+        nout = self.w_head.shape[0]
+        tok = torch.empty(rows, nout, dtype=F32, device=self.device)
+        mv.head_tokens(ws.x[:rows], em[0].contiguous(), em[1].contiguous(), self.w_head, self.b_head, tok, self.eps)
+        full = grp.all_gather_rows(tok)
+        out = torch.empty(self.out_dim, grid[0], grid[1] * self.patch[1], grid[2] * self.patch[2], dtype=F32,
+                          device=self.device)
+        mv.unpatchify(full, out, grid, (self.patch[1], self.patch[2]))
         return out

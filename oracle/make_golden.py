@@ -1,0 +1,135 @@
+"""Mints tests/golden/*.pt from the REAL reference code (/root/reference, imported through oracle/ref_loader.py).
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python oracle/make_golden.py
+The reference ships no tests or golden vectors; these files pin the oracle (and, on the GPU, the
+CUDA path) to the reference's own forward code on fixed seeds.  fp32, CPU, SDPA in place of flash-attn.
+"""
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from oracle.fill import fill_parameters  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_block_cfg1(model):
+    """BASELINE.json configs[0]: single WanAttentionBlock, dim 128, 1x16x16 token grid (256 tokens)."""
+    torch.manual_seed(0)
+    blk = model.WanAttentionBlock("t2v_cross_attn", 128, 512, 4, (-1, -1), True, True, 1e-6).eval()
+    fill_parameters(blk, 101)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 256, 128, generator=g)
+    e = torch.randn(1, 6, 128, generator=g)
+    ctx = torch.randn(1, 512, 128, generator=g)
+    dh = 32
+    freqs = torch.cat([model.rope_params(1024, dh - 4 * (dh // 6)), model.rope_params(1024, 2 * (dh // 6)),
+                       model.rope_params(1024, 2 * (dh // 6))], 1)
+    with torch.no_grad():
+        y = blk(x, e, torch.tensor([256]), torch.tensor([[1, 16, 16]]), freqs, ctx, None)
+    return dict(x=x, e=e, ctx=ctx, y=y, seed=101, grid=(1, 16, 16),
+                param_shapes={k: tuple(v.shape) for k, v in blk.state_dict().items()})
+
+
+TINY = dict(model_type="t2v", patch_size=(1, 2, 2), text_len=16, in_dim=16, dim=256, ffn_dim=512, freq_dim=64,
+            text_dim=64, out_dim=16, num_heads=2, num_layers=2, qk_norm=True, cross_attn_norm=True, eps=1e-6)
+
+
+def golden_model_tiny(model):
+    """Tiny WanModel with head_dim 128 (what the sm_100a attention kernel supports): 2 layers, 32 real tokens padded to 40."""
+    m = model.WanModel(**TINY).eval()
+    fill_parameters(m, 202)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(16, 2, 8, 8, generator=g)
+    ctx = torch.randn(11, 64, generator=g)
+    t = torch.tensor([642])
+    outs = {}
+    with torch.no_grad():
+        for seq_len in (32, 40):
+            outs[seq_len] = m([x], t, [ctx], seq_len)[0]
+    return dict(cfg=TINY, x=x, ctx=ctx, t=t, y32=outs[32], y40=outs[40], seed=202,
+                param_shapes={k: tuple(v.shape) for k, v in m.state_dict().items()})
+
+
+def golden_unipc():
+    """Trajectory of the reference FlowUniPCMultistepScheduler on a fixed pseudo-model (needs a fuller diffusers stub)."""
+    du = types.ModuleType("diffusers.utils")
+    du.deprecate = lambda *a, **k: None
+    du.is_scipy_available = lambda: False
+    sch = types.ModuleType("diffusers.schedulers")
+    su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+
+    class SchedulerMixin:
+        pass
+
+    class SchedulerOutput(dict):
+        pass
+
+    class _K:
+        name = "x"
+
+    su.KarrasDiffusionSchedulers = [_K]
+    su.SchedulerMixin, su.SchedulerOutput = SchedulerMixin, SchedulerOutput
+
+    class ConfigMixin:
+        pass
+
+    def register_to_config(init):
+        def wrapped(self, *a, **k):
+            import inspect
+            sig = inspect.signature(init)
+            ba = sig.bind(self, *a, **k)
+            ba.apply_defaults()
+            cfg = types.SimpleNamespace(**{n: v for n, v in ba.arguments.items() if n != "self"})
+            self.config = cfg
+            self.register_to_config = lambda **kw: [setattr(cfg, a_, b_) for a_, b_ in kw.items()]
+            init(self, *a, **k)
+        return wrapped
+
+    cu = sys.modules["diffusers.configuration_utils"]
+    cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+    sys.modules["diffusers.utils"] = du
+    sys.modules["diffusers.schedulers"] = sch
+    sys.modules["diffusers.schedulers.scheduling_utils"] = su
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location(
+        "refwan_unipc", os.path.join(ref_loader.REF_ROOT, "wan", "utils", "fm_solvers_unipc.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = {}
+    for steps in (4, 9):
+        s = mod.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        s.set_timesteps(steps, device="cpu", shift=5.0)
+        g = torch.Generator().manual_seed(steps)
+        x = torch.randn(1, 16, 2, 4, 4, generator=g)
+        traj, outs = [x.clone()], []
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints debug lines every step
+            for t in s.timesteps:
+                v = torch.sin(3.0 * x) * 0.5 + 0.1 * torch.randn(x.shape, generator=g)  # pseudo model output
+                outs.append(v)
+                x = s.step(v, t, x, return_dict=False)[0]
+                traj.append(x.clone())
+        res[steps] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), model_outputs=outs, traj=traj)
+    return res
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    att, model, vae = ref_loader.load_reference()
+    torch.save(golden_block_cfg1(model), os.path.join(OUT, "block_cfg1.pt"))
+    torch.save(golden_model_tiny(model), os.path.join(OUT, "model_tiny_hd128.pt"))
+    torch.save(golden_unipc(), os.path.join(OUT, "unipc.pt"))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""CPU: the oracle (oracle/dit_oracle.py) and the host-side restatements are pinned against golden vectors minted
+from the reference's own code by oracle/make_golden.py (the reference has no tests of its own)."""
+import os
+
+import pytest
+import torch
+
+from oracle import dit_oracle as O
+from oracle.fill import state_dict_like
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def test_oracle_block_config1_matches_reference():
+    """BASELINE.json configs[0]: one WanAttentionBlock, dim 128, 256 tokens, fp32, CPU."""
+    g = load("block_cfg1.pt")
+    sd = {"blk." + k: v for k, v in state_dict_like(g["param_shapes"], g["seed"]).items()}
+    angles = O.rope_table(g["grid"], 32, 256)
+    y = O.block_forward(sd, "blk.", g["x"][0], g["e"][0], angles, g["ctx"][0], 4, 1e-6, O.ident, k_len=256)
+    # fp32 vs fp32 (different summation orders only): 1e-5 relative
+    assert ((y - g["y"][0]).norm() / g["y"][0].norm()).item() < 1e-5
+    assert (y - g["y"][0]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("seq_len", [32, 40])
+def test_oracle_tiny_model_matches_reference(seq_len):
+    g = load("model_tiny_hd128.pt")
+    sd = state_dict_like(g["param_shapes"], g["seed"])
+    y = O.model_forward(sd, g["cfg"], g["x"], g["t"][0], g["ctx"], seq_len, O.ident)
+    ref = g["y%d" % seq_len]
+    assert y.shape == ref.shape
+    assert ((y - ref).norm() / ref.norm()).item() < 1e-5
+
+
+def test_bf16_emulation_is_close_to_fp32_reference():
+    """The bf16 cast points the kernels implement stay within the §8c block tolerance of the fp32 reference."""
+    g = load("model_tiny_hd128.pt")
+    sd = state_dict_like(g["param_shapes"], g["seed"])
+    y = O.model_forward(sd, g["cfg"], g["x"], g["t"][0], g["ctx"], 40, O.bf16_rt)
+    rel = ((y - g["y40"]).norm() / g["y40"].norm()).item()
+    assert rel < 1e-2, rel
+
+
+def test_wan_model_state_dict_matches_reference_names():
+    """Reference checkpoints must load: same parameter names and shapes."""
+    from wan.modules.model import WanModel
+    g = load("model_tiny_hd128.pt")
+    cfg = dict(g["cfg"])
+    m = WanModel(**cfg)
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ours == g["param_shapes"]
+
+
+def test_unipc_scheduler_matches_reference():
+    from wan.utils.fm_solvers_unipc import FlowUniPCMultistepScheduler
+    gold = load("unipc.pt")
+    for steps, rec in gold.items():
+        s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        s.set_timesteps(steps, device="cpu", shift=5.0)
+        assert torch.equal(s.timesteps, rec["timesteps"])
+        assert torch.equal(s.sigmas, rec["sigmas"])
+        x = rec["traj"][0]
+        for i, t in enumerate(s.timesteps):
+            x = s.step(rec["model_outputs"][i], t, x, return_dict=False)[0]
+            ref = rec["traj"][i + 1]
+            assert (x - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), (steps, i)
+
+
+def test_rope_table_matches_engine_table():
+    """The engine's fp32 cos/sin table (built from the complex128 freqs like the reference) equals the oracle angles."""
+    from wan.modules.engine import rope_cos_sin
+    from wan.modules.model import rope_params
+    d = 128
+    freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
+                       rope_params(1024, 2 * (d // 6))], dim=1)
+    grid, seq_len = (3, 4, 5), 64
+    cs = rope_cos_sin(freqs, grid, seq_len)
+    ang = O.rope_table(grid, d, seq_len)
+    assert cs.shape == (seq_len, d // 2, 2)
+    assert (cs[..., 0].double() - torch.cos(ang)).abs().max() < 1e-6
+    assert (cs[..., 1].double() - torch.sin(ang)).abs().max() < 1e-6
+    part = rope_cos_sin(freqs, grid, seq_len, start=16, rows=16)
+    assert torch.equal(part, cs[16:32])
