@@ -38,6 +38,7 @@ typedef void* mv_stream_t; /* cudaStream_t */
 #define MV_EPI_BF16_GELU 1  /* out_bf16[m,n]  = bf16(gelu_tanh(float(y)))           (model.py:267-268)         */
 #define MV_EPI_RESID_F32 2  /* out_f32[m,n]  += float(y) * (gate ? gate[n] : 1)     (model.py:302,306,309)     */
 #define MV_EPI_F32_ROUND 3  /* out_f32[m,n]   = float(y)                            (model.py:529)             */
+#define MV_EPI_F32 4        /* out_f32[m,n]   = acc + bias (no bf16 rounding; VAE attention scores, vae.py:252) */
 
 const char* mv_last_error(void);
 int mv_version(void);
@@ -123,7 +124,36 @@ int mv_linear_f32_vec(const float* x, const float* W, const float* b, float* out
 int mv_sinusoid_embed(const void* t, int t_is_int64, float* out, int dim, mv_stream_t stream);
 
 /* ---- WanVAE decoder (wan/modules/vae.py) ------------------------------------------------------- */
-/* declared in the VAE section of the library when built; see DESIGN.md for status. */
+/* Activations are channels-last bf16 [T, H, W, C]; weights are packed per conv as bf16 [Cout_pad][tap][Cin]. */
+
+/* Stride-1 "same" convolution as an implicit GEMM on tcgen05 (csrc/vae_conv_sm100.cu):
+ *   out[t,h,w,:] = bias + sum_i in[t+dt_i, h+dh_i, w+dw_i, :] . W[:, i, :]^T (+ res[t,h,w,:])
+ * with zero fill outside the input grid (spatial zero padding and the causal temporal padding of
+ * CausalConv3d, vae.py:17-36).  taps = ntaps (dt,dh,dw) int8 triples (host memory).  The output element offset of
+ * voxel (t,h,w) is o_base + t*os_t + h*os_h + w*os_w, which expresses the sub-pixel (nearest-2x + Conv2d,
+ * vae.py:74-79) and frame-interleave (time_conv, vae.py:128-137) stores; output channel blocks >= nsplit are
+ * written to channel (n - nsplit) at offset + nsplit_off (nsplit = 0 disables).
+ * out_mode 0: bf16 channels-last (+ optional bf16 residual with the same addressing);
+ * out_mode 1: fp32 channel-first [cout_real, T, H, W] clamped to [-1, 1] (decoder head, vae.py:465-471,660-661). */
+int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed, const float* bias,
+                const void* res_cl, void* out, int out_mode, int out_T, int out_H, int out_W, int Cout, int cout_real,
+                int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t, int64_t os_h, int64_t os_w,
+                int nsplit, int64_t nsplit_off, mv_stream_t stream);
+
+/* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per voxel over channels (RMS_norm + nn.SiLU,
+ * vae.py:39-54,194-199); channels-last bf16, in place allowed. */
+int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,
+                        mv_stream_t stream);
+
+/* x_cl[v, o] = sum_c W2[o,c] * (z[c, v] * std[c] + mean[c]) + b2[o]: latent de-normalisation + conv2 (1x1x1) +
+ * fp32 channel-first -> bf16 channels-last (vae.py:547-553,629-639). */
+int mv_vae_latent_in(const float* z, const float* W2, const float* b2, const float* mean, const float* stdv,
+                     void* out_cl, int Z, int64_t nvox, mv_stream_t stream);
+
+/* P_bf16[m, :N] = softmax(S[m, :N] * scale) (fp32 in): the softmax of the VAE's single-head attention between the
+ * two tcgen05 GEMMs (vae.py:246-257). */
+int mv_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int M, int N, float scale,
+                    mv_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -168,7 +168,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 32; ++i) {
             float b = 0.f;
             if (p.bias != nullptr && col0 + i < p.N) b = __ldg(p.bias + col0 + i);
-            v[i] = bf16_round(__uint_as_float(r[i]) + b);
+            v[i] = __uint_as_float(r[i]) + b;
+            if constexpr (EPI != MV_EPI_F32) v[i] = bf16_round(v[i]);
           }
           const bool full_chunk = (col0 + 32 <= p.N);
           if constexpr (EPI == MV_EPI_BF16 || EPI == MV_EPI_BF16_GELU) {
@@ -269,8 +270,8 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
   MV_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "mv_gemm_bf16: K/lda/ldw must be multiples of 8 (K=%d lda=%lld ldw=%lld)",
              K, (long long)lda, (long long)ldw);
   MV_REQUIRE(lda >= (a_kblock > 0 ? a_kblock : K) && ldw >= K && ldo >= N, "mv_gemm_bf16: leading dimensions too small");
-  MV_REQUIRE(epilogue >= 0 && epilogue <= 3, "mv_gemm_bf16: unknown epilogue %d", epilogue);
-  const bool f32_out = (epilogue == MV_EPI_RESID_F32 || epilogue == MV_EPI_F32_ROUND);
+  MV_REQUIRE(epilogue >= 0 && epilogue <= 4, "mv_gemm_bf16: unknown epilogue %d", epilogue);
+  const bool f32_out = (epilogue == MV_EPI_RESID_F32 || epilogue == MV_EPI_F32_ROUND || epilogue == MV_EPI_F32);
   MV_REQUIRE(ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "mv_gemm_bf16: output must be 16-byte aligned with 16-byte aligned rows");
   MV_REQUIRE(gate == nullptr || (reinterpret_cast<uintptr_t>(gate) & 15) == 0, "mv_gemm_bf16: gate must be 16B aligned");
@@ -316,6 +317,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
     case MV_EPI_BF16: return launch_gemm<MV_EPI_BF16>(tmA, tmB, p, st);
     case MV_EPI_BF16_GELU: return launch_gemm<MV_EPI_BF16_GELU>(tmA, tmB, p, st);
     case MV_EPI_RESID_F32: return launch_gemm<MV_EPI_RESID_F32>(tmA, tmB, p, st);
+    case MV_EPI_F32: return launch_gemm<MV_EPI_F32>(tmA, tmB, p, st);
     default: return launch_gemm<MV_EPI_F32_ROUND>(tmA, tmB, p, st);
   }
 }

@@ -70,6 +70,23 @@ static PFN_encodeTiled get_encode() {
 
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  return make_tmap_bf16_sw(map, base, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0);
+}
+
+int make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 128) swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (swizzle_bytes == 64) swz = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 32) swz = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes != 0) {
+    set_error("unsupported TMA swizzle span %d", swizzle_bytes);
+    return MV_E_SHAPE;
+  }
+  if (swizzle_bytes != 0 && static_cast<int>(box[0]) * 2 != swizzle_bytes) {
+    set_error("TMA box inner extent %u B does not match the swizzle span %d B", box[0] * 2, swizzle_bytes);
+    return MV_E_SHAPE;
+  }
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -98,7 +115,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                    gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)",

@@ -21,6 +21,9 @@ int sm_count();
 // (dim 0 is contiguous).  Swizzle 128B requires box[0] * 2 bytes == 128.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+// Same with an explicit swizzle span: 128, 64, 32 (bytes; must equal box[0] * 2) or 0 (none).
+int make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 #define MV_CHECK_CUDA(expr)                                \
   do {                                                     \

@@ -1,0 +1,500 @@
+// WanVAE decoder convolutions as an implicit GEMM on tcgen05 (channels-last bf16 activations).
+//
+//   out[t,h,w,:] = bias + sum_taps  in[t+dt, h+dh, w+dw, :] . Wtap^T        (+ residual)
+//
+// M tile = 128 output voxels = an 8 x 16 (h x w) patch of one frame.  For every tap and every block of BK input
+// channels the A operand is ONE 4-D TMA box {BK, 16, 8, 1} of the input tensor at the shifted coordinate — the
+// hardware's out-of-bounds zero fill implements the spatial zero padding and the causal temporal padding (frames
+// before the first are zero, vae.py:17-36), and the box lands in shared memory already in the 128-row K-major
+// swizzled layout tcgen05.mma wants ("im2col staging" without an im2col buffer).  B = the tap's weight slab
+// [Cout_tile, BK] of the pre-packed matrix W[Cout][tap][Cin].  fp32 accumulation in TMEM (2 stages), persistent
+// CTAs, warp-specialised exactly like gemm_sm100.cu.
+//
+// Serves CausalConv3d 3x3x3 / 1x1x1 (vae.py:17-36), the Conv2d 3x3 after nearest-2x upsampling as four 2x2
+// sub-pixel convolutions on the low-resolution input (vae.py:74-79: the nearest-exact x2 + 3x3 kernel collapses to
+// a 2x2 kernel per output parity, 2.25x fewer FLOPs and no upsampled intermediate), the temporal time_conv
+// (3,1,1) with its frame interleave (vae.py:84-85,128-137) and the 96->3 head conv with the final clamp.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mv {
+
+constexpr int kConvBM = 128;
+constexpr int kConvTW = 16;   // tile width  (w)
+constexpr int kConvTH = 8;    // tile height (h)
+constexpr int kConvStages = 5;
+constexpr int kConvThreads = 192;
+constexpr int kConvMaxTaps = 27;
+constexpr uint32_t kConvABytesMax = kConvBM * 64 * 2;   // 16 KB
+constexpr uint32_t kConvBBytesMax = 256 * 64 * 2;       // 32 KB
+constexpr uint32_t kConvSmem = kConvStages * (kConvABytesMax + kConvBBytesMax) + 1024 + 256;
+
+struct ConvParams {
+  const float* bias;            // [Cout] or null
+  const __nv_bfloat16* res;     // residual, same addressing as out (bf16 channels-last) or null
+  void* out;
+  // output addressing (elements): off = base + t*os_t + h*os_h + w*os_w (+ parity remap) + channel
+  int64_t o_base, os_t, os_h, os_w;
+  int nsplit;                   // > 0: output channel block n0 >= nsplit goes to (n0 - nsplit) with + nsplit_off
+  int64_t nsplit_off;
+  int T, H, W;                  // output grid (== input grid: stride-1 "same" convolutions)
+  int Cin, Cout;
+  int BN;                       // N tile (multiple of 16, <= 256)
+  int ntaps;
+  int8_t dt[kConvMaxTaps], dh[kConvMaxTaps], dw[kConvMaxTaps];
+  int num_n, tiles_h, tiles_w, num_tiles, kblocks_per_tap;
+  int out_mode;                 // 0: bf16 channels-last; 1: fp32 channel-first video [Cout_real,T,H,W] clamped to [-1,1]
+  int cout_real;                // out_mode 1: number of real output channels (3)
+};
+
+template <int BK>
+struct ConvCfg {
+  static constexpr uint32_t kRowBytes = BK * 2;
+  static constexpr uint32_t kLayout = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);  // 128B / 64B / 32B swizzle
+  static constexpr uint32_t kSBO = 8 * kRowBytes;
+  static constexpr uint32_t kABytes = kConvBM * kRowBytes;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+  using Cfg = ConvCfg<BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kConvStages * kConvABytesMax;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConvStages * (kConvABytesMax + kConvBBytesMax));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kConvStages;
+  uint64_t* tfull = bars + 2 * kConvStages;
+  uint64_t* tempty = bars + 2 * kConvStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConvStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * Cfg::kRowBytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kConvStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kb_total = p.ntaps * p.kblocks_per_tap;
+
+  // tile -> (n block fastest, then w, h, t): CTAs running together share the same input patch through L2
+  auto decode = [&](int tile, int& n_blk, int& t, int& h0, int& w0) {
+    n_blk = tile % p.num_n;
+    int r = tile / p.num_n;
+    w0 = (r % p.tiles_w) * kConvTW;
+    r /= p.tiles_w;
+    h0 = (r % p.tiles_h) * kConvTH;
+    t = r / p.tiles_h;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int n_blk, t, h0, w0;
+        decode(tile, n_blk, t, h0, w0);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], Cfg::kABytes + b_bytes);
+            tma_load_4d(sA + stage * kConvABytesMax, &tmA, &full[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap],
+                        t + p.dt[tap]);
+            tma_load_2d(sB + stage * kConvBBytesMax, &tmB, &full[stage], tap * p.Cin + cb * BK, n_blk * p.BN);
+            if (++stage == kConvStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kConvBM, static_cast<uint32_t>(p.BN), 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * kConvABytesMax), 16, Cfg::kSBO, Cfg::kLayout);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * kConvBBytesMax), 16, Cfg::kSBO, Cfg::kLayout);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == kConvStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    const int r = quad * 32 + lane;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int n_blk, t, h0, w0;
+      decode(tile, n_blk, t, h0, w0);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int h = h0 + (r >> 4), w = w0 + (r & 15);
+      const bool ok = (h < p.H) && (w < p.W);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256;
+      int n0 = n_blk * p.BN;
+      int64_t off = p.o_base + t * p.os_t + h * p.os_h + w * p.os_w;
+      int nb = n0;  // channel offset inside the destination row
+      if (p.nsplit > 0 && n0 >= p.nsplit) {
+        nb = n0 - p.nsplit;
+        off += p.nsplit_off;
+      }
+      for (int c = 0; c < p.BN; c += 32) {   // BN multiple of 16: last chunk may be half valid
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c, v);
+        tc_wait_ld();
+        const int ncols = min(32, p.BN - c);
+        if (ok) {
+          if (p.out_mode == 0) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float b = (p.bias != nullptr && i < ncols && n0 + c + i < p.Cout) ? __ldg(p.bias + n0 + c + i) : 0.f;
+              f[i] = __uint_as_float(v[i]) + b;
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + nb + c;
+            if (p.res != nullptr) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + nb + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (8 * i < ncols) {
+                  const uint4 q = r4[i];
+                  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    f[8 * i + 2 * k] += bf16_lo(u[k]);
+                    f[8 * i + 2 * k + 1] += bf16_hi(u[k]);
+                  }
+                }
+              }
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (8 * i < ncols) {
+                uint4 q;
+                q.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+                q.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+                q.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+                q.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                o4[i] = q;
+              }
+            }
+          } else {
+            // head conv: fp32 channel-first video, clamp(-1, 1)                       vae.py:660-661
+            float* o = reinterpret_cast<float*>(p.out);
+            const int64_t plane = static_cast<int64_t>(p.T) * p.H * p.W;
+            const int64_t pos = (static_cast<int64_t>(t) * p.H + h) * p.W + w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (c == 0 && i < p.cout_real) {
+                float b = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+                float y = __uint_as_float(v[i]) + b;
+                y = fminf(1.f, fmaxf(-1.f, y));
+                o[i * plane + pos] = y;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// RMS_norm over channels + SiLU, channels-last bf16 -> bf16 (in place allowed).   vae.py:39-54 + nn.SiLU
+// y = silu( x / max(||x||_2, 1e-12) * sqrt(C) * gamma (+ beta) );  one warp per voxel, C <= 512, C % 8 == 0.
+// silu == 0 skips the activation (AttentionBlock.norm, vae.py:233,246).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                       int64_t nvox, int C, int silu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = C >> 3;
+  const float scale = sqrtf(static_cast<float>(C));
+  for (int64_t vox = warp0; vox < nvox; vox += nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + vox * C);
+    uint4 a[2];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = lane + 32 * j;
+      if (idx < nvec) {
+        a[j] = xr[idx];
+        const uint32_t u[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = bf16_lo(u[k]), hi = bf16_hi(u[k]);
+          ss += lo * lo + hi * hi;
+        }
+      }
+    }
+    ss = warp_sum(ss);
+    const float inv = scale / fmaxf(sqrtf(ss), 1e-12f);
+    uint4* yr = reinterpret_cast<uint4*>(y + vox * C);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = lane + 32 * j;
+      if (idx < nvec) {
+        uint32_t u[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float lo = bf16_lo(u[k]) * inv * g[2 * k];
+          float hi = bf16_hi(u[k]) * inv * g[2 * k + 1];
+          if (silu) {
+            lo = lo / (1.f + __expf(-lo));
+            hi = hi / (1.f + __expf(-hi));
+          }
+          u[k] = pack_bf16(lo, hi);
+        }
+        yr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Latent de-normalisation + conv2 (1x1x1, 16 -> 16) + layout change to channels-last bf16.
+// x[t,h,w,o] = sum_c W2[o,c] * (z[c,t,h,w] * std[c] + mean[c]) + b2[o]                vae.py:547-553
+// --------------------------------------------------------------------------------------------
+__global__ void vae_latent_in_kernel(const float* __restrict__ z, const float* __restrict__ W2, const float* __restrict__ b2,
+                                     const float* __restrict__ mean, const float* __restrict__ stdv,
+                                     __nv_bfloat16* __restrict__ out, int Z, int64_t nvox) {
+  __shared__ float sw[32 * 32 + 96];
+  float* sb = sw + Z * Z;
+  float* sm = sb + Z;
+  float* ss = sm + Z;
+  for (int i = threadIdx.x; i < Z * Z; i += blockDim.x) sw[i] = W2[i];
+  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
+    sb[i] = b2[i];
+    sm[i] = mean[i];
+    ss[i] = stdv[i];
+  }
+  __syncthreads();
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float zin[32];
+    for (int c = 0; c < Z; ++c) zin[c] = z[c * nvox + v] * ss[c] + sm[c];
+    for (int o = 0; o < Z; ++o) {
+      float acc = sb[o];
+      for (int c = 0; c < Z; ++c) acc = fmaf(sw[o * Z + c], zin[c], acc);
+      out[v * Z + o] = __float2bfloat16_rn(acc);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Row softmax for the VAE's single-head attention: P = softmax(S * scale), S fp32 [M, N] -> P bf16 [M, ldp].
+// One CTA per row.                                                                 vae.py:246-257
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, int64_t lds, __nv_bfloat16* __restrict__ P, int64_t ldp, int N,
+                    float scale) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float* s = S + row * lds;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, s[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sum += __expf((s[i] - mx) * scale);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  __nv_bfloat16* pr = P + row * ldp;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) pr[i] = __float2bfloat16_rn(__expf((s[i] - mx) * scale) * inv);
+}
+
+template <int BK>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kConvSmem)));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_igemm_kernel<BK><<<grid, kConvThreads, kConvSmem, st>>>(tmA, tmB, p);
+  MV_CHECK_LAUNCH("conv_igemm_kernel");
+  return MV_OK;
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
+                           const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
+                           int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
+                           int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
+                           mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(ntaps >= 1 && ntaps <= kConvMaxTaps, "mv_vae_conv: ntaps=%d out of range", ntaps);
+  MV_REQUIRE(Cin % 16 == 0 && Cin >= 16, "mv_vae_conv: Cin=%d must be a multiple of 16", Cin);
+  MV_REQUIRE(Cout % 16 == 0, "mv_vae_conv: (padded) Cout=%d must be a multiple of 16", Cout);
+  MV_REQUIRE(out_T > 0 && out_H > 0 && out_W > 0, "mv_vae_conv: empty output grid");
+  int BK = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+  int BN;
+  if (Cout <= 256) BN = Cout;
+  else if (Cout % 192 == 0) BN = 192;
+  else if (Cout % 256 == 0) BN = 256;
+  else if (Cout % 128 == 0) BN = 128;
+  else {
+    set_error("mv_vae_conv: cannot tile Cout=%d", Cout);
+    return MV_E_SHAPE;
+  }
+  MV_REQUIRE(nsplit == 0 || nsplit % BN == 0, "mv_vae_conv: nsplit must be a multiple of the N tile");
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
+    uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)Cin * in_W * 2, (uint64_t)Cin * in_W * in_H * 2};
+    uint32_t box[4] = {(uint32_t)BK, kConvTW, kConvTH, 1};
+    rc = make_tmap_bf16_sw(&tmA, in_cl, 4, dims, str, box, BK * 2);
+    if (rc != MV_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ntaps * Cin, (uint64_t)Cout};
+    uint64_t str[2] = {2, (uint64_t)ntaps * Cin * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    rc = make_tmap_bf16_sw(&tmB, w_packed, 2, dims, str, box, BK * 2);
+    if (rc != MV_OK) return rc;
+  }
+  ConvParams p;
+  p.bias = bias;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res_cl);
+  p.out = out;
+  p.o_base = o_base;
+  p.os_t = os_t;
+  p.os_h = os_h;
+  p.os_w = os_w;
+  p.nsplit = nsplit;
+  p.nsplit_off = nsplit_off;
+  p.T = out_T;
+  p.H = out_H;
+  p.W = out_W;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.BN = BN;
+  p.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) {
+    p.dt[i] = taps_dt_dh_dw[3 * i];
+    p.dh[i] = taps_dt_dh_dw[3 * i + 1];
+    p.dw[i] = taps_dt_dh_dw[3 * i + 2];
+  }
+  p.num_n = Cout / BN;
+  p.tiles_h = (out_H + kConvTH - 1) / kConvTH;
+  p.tiles_w = (out_W + kConvTW - 1) / kConvTW;
+  const int64_t nt = static_cast<int64_t>(p.num_n) * p.tiles_h * p.tiles_w * out_T;
+  MV_REQUIRE(nt < (1ll << 31), "mv_vae_conv: too many tiles");
+  p.num_tiles = static_cast<int>(nt);
+  p.kblocks_per_tap = Cin / BK;
+  p.out_mode = out_mode;
+  p.cout_real = cout_real;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BK == 64) return launch_conv<64>(tmA, tmB, p, st);
+  if (BK == 32) return launch_conv<32>(tmA, tmB, p, st);
+  return launch_conv<16>(tmA, tmB, p, st);
+}
+
+extern "C" int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,
+                                   mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(nvox > 0 && C > 0 && C % 8 == 0 && C <= 512, "mv_vae_rmsnorm_silu: bad shape nvox=%lld C=%d", (long long)nvox, C);
+  int64_t blocks = (nvox + 7) / 8;
+  if (blocks > sm_count() * 32) blocks = sm_count() * 32;
+  rmsnorm_silu_cl_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_cl), reinterpret_cast<__nv_bfloat16*>(y_cl), gamma, nvox, C, silu);
+  MV_CHECK_LAUNCH("rmsnorm_silu_cl_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_vae_latent_in(const float* z, const float* W2, const float* b2, const float* mean, const float* stdv,
+                                void* out_cl, int Z, int64_t nvox, mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(Z > 0 && Z <= 32 && nvox > 0, "mv_vae_latent_in: bad shape");
+  int64_t blocks = (nvox + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  vae_latent_in_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, W2, b2, mean, stdv, reinterpret_cast<__nv_bfloat16*>(out_cl), Z, nvox);
+  MV_CHECK_LAUNCH("vae_latent_in_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int M, int N, float scale,
+                               mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(M > 0 && N > 0, "mv_softmax_rows: empty problem");
+  softmax_rows_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, reinterpret_cast<__nv_bfloat16*>(P_bf16),
+                                                                       ldp, N, scale);
+  MV_CHECK_LAUNCH("softmax_rows_kernel");
+  return MV_OK;
+}

@@ -16,6 +16,7 @@ MV_EPI_BF16 = 0
 MV_EPI_BF16_GELU = 1
 MV_EPI_RESID_F32 = 2
 MV_EPI_F32_ROUND = 3
+MV_EPI_F32 = 4
 
 _lib = None
 _c = ctypes
@@ -34,6 +35,11 @@ _SIGNATURES = {
     "mv_qkv_prepare": [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _int, _int, _f32, _ptr],
     "mv_head_tokens": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
     "mv_unpatchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
+    "mv_vae_conv": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
+                    _ptr, _i64, _i64, _i64, _i64, _int, _i64, _ptr],
+    "mv_vae_rmsnorm_silu": [_ptr, _ptr, _ptr, _i64, _int, _int, _ptr],
+    "mv_vae_latent_in": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _ptr],
+    "mv_softmax_rows": [_ptr, _i64, _ptr, _i64, _int, _int, _f32, _ptr],
     "mv_patchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_head_unpatchify": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
                            _f32, _ptr],
@@ -124,7 +130,7 @@ def gemm(a, w, bias, out, epilogue, gate=None):
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
-    want = torch.float32 if epilogue in (MV_EPI_RESID_F32, MV_EPI_F32_ROUND) else torch.bfloat16
+    want = torch.float32 if epilogue in (MV_EPI_RESID_F32, MV_EPI_F32_ROUND, MV_EPI_F32) else torch.bfloat16
     _req(out, want, "out")
     _call("mv_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
                               M, N, K, epilogue, _stream())
@@ -259,3 +265,48 @@ def unpatchify(tokens, out, grid, patch_hw=(2, 2)):
     assert tokens.shape[0] >= F * Hp * Wp and tokens.shape[1] == ph * pw * Cout
     _call("mv_unpatchify", _p(tokens), _p(out), F, Hp, Wp, ph, pw, Cout, _stream())
     return out
+
+
+def vae_conv(x, conv, out, res=None, o_base=0, os_t=0, os_h=0, os_w=0, nsplit=0, nsplit_off=0, out_mode=0):
+    """x [T,H,W,Cin] bf16 channels-last (contiguous); conv: packed weights (.w [Cout,taps,Cin] bf16, .b fp32, .taps int8
+    CPU [ntaps,3]); out: bf16 channels-last (mode 0, any size — addressing by o_base/os_*) or fp32 [3,T,H,W] (mode 1)."""
+    _req(x, torch.bfloat16, "x"); _req(conv.w, torch.bfloat16, "w"); _req(conv.b, torch.float32, "bias")
+    _req(res, torch.bfloat16, "res")
+    assert x.dim() == 4 and x.is_contiguous() and out.is_contiguous() and conv.w.is_contiguous()
+    T, H, W, Cin = x.shape
+    assert Cin == conv.cin and conv.taps.device.type == "cpu" and conv.taps.dtype == torch.int8
+    _req(out, torch.float32 if out_mode == 1 else torch.bfloat16, "out")
+    if res is not None:
+        assert res.is_contiguous() and res.numel() == out.numel()
+    _call("mv_vae_conv", _p(x), T, H, W, Cin, _p(conv.w), _p(conv.b), _p(res), _p(out), int(out_mode), T, H, W,
+          conv.cout, conv.cout_real, conv.ntaps, conv.taps.data_ptr(), int(o_base), int(os_t), int(os_h), int(os_w),
+          int(nsplit), int(nsplit_off), _stream())
+    return out
+
+
+def vae_rmsnorm_silu(x, out, gamma, silu=True):
+    _req(x, torch.bfloat16, "x"); _req(out, torch.bfloat16, "out"); _req(gamma, torch.float32, "gamma")
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and gamma.numel() == x.shape[-1]
+    C = x.shape[-1]
+    _call("mv_vae_rmsnorm_silu", _p(x), _p(out), _p(gamma), x.numel() // C, C, int(bool(silu)), _stream())
+    return out
+
+
+def vae_latent_in(z, w2, b2, mean, std, out):
+    for t, n in ((z, "z"), (w2, "w2"), (b2, "b2"), (mean, "mean"), (std, "std")):
+        _req(t, torch.float32, n)
+        assert t.is_contiguous()
+    _req(out, torch.bfloat16, "out")
+    Z = z.shape[0]
+    nvox = z.numel() // Z
+    assert out.is_contiguous() and out.numel() == z.numel() and out.shape[-1] == Z
+    _call("mv_vae_latent_in", _p(z), _p(w2), _p(b2), _p(mean), _p(std), _p(out), Z, nvox, _stream())
+    return out
+
+
+def softmax_rows(s, p, n, scale):
+    _req(s, torch.float32, "s"); _req(p, torch.bfloat16, "p")
+    assert s.dim() == 2 and p.dim() == 2 and s.stride(1) == 1 and p.stride(1) == 1 and s.shape[0] == p.shape[0]
+    assert s.shape[1] >= n and p.shape[1] >= n
+    _call("mv_softmax_rows", _p(s), s.stride(0), _p(p), p.stride(0), s.shape[0], n, float(scale), _stream())
+    return p

@@ -1,15 +1,314 @@
-"""WanVAE (decoder) — placeholder until the native 3-D causal-conv decoder lands (see DESIGN.md status table)."""
+"""WanVAE with the reference's wrapper surface (wan/modules/vae.py:619-663) and decoder parameter names, decoded
+by the B200-native implicit-GEMM kernels (csrc/vae_conv_sm100.cu) through the C ABI.
+
+Scope: the DECODER (WanVAE.decode) — the encoder is preprocessing only and out of scope.
+The decode is one pass over the whole latent sequence (the reference's 21 single-frame chunks + feature cache are
+a causal network; the only irregularity — upsample3d's time_conv starting at frame 1, the 'Rep' branch — is
+reproduced exactly; SURVEY.md Appendix B, pinned by tests/golden/vae_*.pt).
+Activations are channels-last bf16 [T, H, W, C]; accumulation is fp32.
+"""
+import logging
+import math
+
 import torch
+import torch.nn as nn
+
+import movii_b200 as mv
+
+__all__ = ["WanVAE"]
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+VAE_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632,
+            -0.1922, -0.9497, 0.2503, -0.2921]
+VAE_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526, 2.8652, 1.5579, 1.6382,
+           1.1253, 2.8251, 1.9160]
 
 
-class _Dims:
-    z_dim = 16
+# ------------------------------------------------------------------------------------------------
+# parameter holders (names == reference state-dict keys)
+# ------------------------------------------------------------------------------------------------
+class _Gamma(nn.Module):
+    def __init__(self, dim, images):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones((dim, 1, 1) if images else (dim, 1, 1, 1)))
+
+
+class _Res(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.residual = nn.Sequential(_Gamma(cin, False), nn.Identity(), nn.Conv3d(cin, cout, 3), _Gamma(cout, False),
+                                      nn.Identity(), nn.Identity(), nn.Conv3d(cout, cout, 3))
+        self.shortcut = nn.Conv3d(cin, cout, 1) if cin != cout else nn.Identity()
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = _Gamma(dim, True)
+        self.to_qkv = nn.Conv2d(dim, dim * 3, 1)
+        self.proj = nn.Conv2d(dim, dim, 1)
+        nn.init.zeros_(self.proj.weight)
+
+
+class _Up(nn.Module):
+    def __init__(self, dim, mode):
+        super().__init__()
+        self.mode = mode
+        self.resample = nn.Sequential(nn.Identity(), nn.Conv2d(dim, dim // 2, 3, padding=1))
+        if mode == "upsample3d":
+            self.time_conv = nn.Conv3d(dim, dim * 2, (3, 1, 1))
+
+
+class _Decoder(nn.Module):
+    def __init__(self, dim, z_dim, dim_mult, num_res_blocks, temperal_upsample):
+        super().__init__()
+        dims = [dim * u for u in [dim_mult[-1]] + list(dim_mult[::-1])]
+        self.conv1 = nn.Conv3d(z_dim, dims[0], 3)
+        self.middle = nn.Sequential(_Res(dims[0], dims[0]), _Attn(dims[0]), _Res(dims[0], dims[0]))
+        ups = []
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            if i in (1, 2, 3):
+                cin = cin // 2
+            for _ in range(num_res_blocks + 1):
+                ups.append(_Res(cin, cout))
+                cin = cout
+            if i != len(dim_mult) - 1:
+                ups.append(_Up(cout, "upsample3d" if temperal_upsample[i] else "upsample2d"))
+        self.upsamples = nn.Sequential(*ups)
+        self.head = nn.Sequential(_Gamma(dims[-1], False), nn.Identity(), nn.Conv3d(dims[-1], 3, 3))
+
+
+class WanVAE_(nn.Module):
+    """Decoder half of the reference's WanVAE_ (vae.py:481-514): `conv2` + `decoder`, same parameter names."""
+
+    def __init__(self, dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_downsample=(False, True, True), dropout=0.0):
+        super().__init__()
+        if len(attn_scales) != 0:
+            raise NotImplementedError("attn_scales must be empty (the shipped VAE config, vae.py:597-604)")
+        self.dim, self.z_dim = dim, z_dim
+        self.temperal_upsample = tuple(temperal_downsample)[::-1]
+        self.conv2 = nn.Conv3d(z_dim, z_dim, 1)
+        self.decoder = _Decoder(dim, z_dim, tuple(dim_mult), num_res_blocks, self.temperal_upsample)
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = VaeEngine(self)
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._engine = None
+        return r
+
+    def load_state_dict(self, sd, strict=True, **k):
+        """Reference checkpoints also carry the encoder (`encoder.*`, `conv1.*`): out of scope, dropped here."""
+        sd = {n: v for n, v in sd.items() if n.startswith("decoder.") or n.startswith("conv2.")}
+        r = super().load_state_dict(sd, strict=strict, **k)
+        self._engine = None
+        return r
+
+    def decode(self, z, scale=None):
+        """z [1, z_dim, T, h, w] -> [1, 3, 1+4(T-1), 8h, 8w] (vae.py:544-568); scale is accepted for API parity and
+        must be the standard (mean, 1/std) pair."""
+        return self.engine().decode(z[0]).unsqueeze(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine
+# ------------------------------------------------------------------------------------------------
+def _taps(kt, kh, kw):
+    """(dt, dh, dw) per tap in weight order; temporal taps are causal (vae.py:24-36)."""
+    return [(it - 2 * (kt // 2), ih - kh // 2, iw - kw // 2) for it in range(kt) for ih in range(kh) for iw in range(kw)]
+
+
+class _Conv:
+    """One packed convolution: bf16 [Cout_pad][taps][Cin] + fp32 bias + tap offsets."""
+
+    def __init__(self, weight, bias, taps, device, cout_pad=None):
+        cout, cin = weight.shape[0], weight.shape[1]
+        w = weight.detach().to(F32).reshape(cout, cin, -1).permute(0, 2, 1).contiguous()      # [Cout, taps, Cin]
+        self.cout_real = cout
+        cp = cout_pad or ((cout + 15) // 16 * 16)
+        if cp != cout:
+            w = torch.cat([w, w.new_zeros(cp - cout, *w.shape[1:])])
+        self.w = w.to(BF16).contiguous().to(device)
+        b = None if bias is None else bias.detach().to(F32)
+        if b is not None and cp != cout:
+            b = torch.cat([b, b.new_zeros(cp - cout)])
+        self.b = None if b is None else b.contiguous().to(device)
+        self.cin, self.cout = cin, cp
+        self.taps = torch.tensor(taps, dtype=torch.int8).contiguous()
+        self.ntaps = len(taps)
+
+
+def _parity_convs(weight, bias, device):
+    """nearest-exact x2 followed by a 3x3 Conv2d == four 2x2 convolutions on the low-res grid, one per output
+    parity (a, b) (vae.py:74-79).  Rows 2h+a-1, 2h+a, 2h+a+1 of the upsampled image are source rows
+    {h-1, h, h} (a=0) or {h, h, h+1} (a=1); the kernel rows falling on the same source row are summed (in fp32)."""
+    groups = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+    w = weight.detach().to(F32)                                                               # [Co, Ci, 3, 3]
+    out = {}
+    for a in (0, 1):
+        for b in (0, 1):
+            taps, mats = [], []
+            for dh, khs in groups[a]:
+                for dw, kws in groups[b]:
+                    taps.append((0, dh, dw))
+                    mats.append(sum(w[:, :, kh, kw] for kh in khs for kw in kws))
+            wp = torch.stack(mats, dim=2).unsqueeze(-1).unsqueeze(-1)                       # [Co, Ci, 4, 1, 1]
+            out[(a, b)] = _Conv(wp, bias, taps, device)
+    return out
+
+
+class VaeEngine:
+    def __init__(self, model):
+        dev = model.conv2.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("WanVAE must live on a CUDA (B200) device: movii_b200 has no CPU path")
+        self.device = dev
+        self.z_dim = model.z_dim
+        d = model.decoder
+        f32 = lambda t: t.detach().to(F32).contiguous().to(dev)  # noqa: E731
+        self.w2 = f32(model.conv2.weight.reshape(self.z_dim, self.z_dim))
+        self.b2 = f32(model.conv2.bias)
+        self.mean = torch.tensor(VAE_MEAN[:self.z_dim], dtype=F32, device=dev)
+        self.std = torch.tensor(VAE_STD[:self.z_dim], dtype=F32, device=dev)
+        self.conv1 = _Conv(d.conv1.weight, d.conv1.bias, _taps(3, 3, 3), dev)
+        self.layers = []
+        for m in list(d.middle) + list(d.upsamples):
+            if isinstance(m, _Res):
+                self.layers.append(("res", self._res(m)))
+            elif isinstance(m, _Attn):
+                self.layers.append(("attn", dict(
+                    gamma=f32(m.norm.gamma.reshape(-1)),
+                    qkv=_Conv(m.to_qkv.weight.unsqueeze(2), m.to_qkv.bias, _taps(1, 1, 1), dev),
+                    proj=_Conv(m.proj.weight.unsqueeze(2), m.proj.bias, _taps(1, 1, 1), dev))))
+            else:
+                up = dict(mode=m.mode, par=_parity_convs(m.resample[1].weight, m.resample[1].bias, dev))
+                if m.mode == "upsample3d":
+                    up["time"] = _Conv(m.time_conv.weight, m.time_conv.bias, _taps(3, 1, 1), dev)
+                self.layers.append(("up", up))
+        self.head_gamma = f32(d.head[0].gamma.reshape(-1))
+        self.head = _Conv(d.head[2].weight, d.head[2].bias, _taps(3, 3, 3), dev, cout_pad=16)
+
+    def _res(self, m):
+        dev = self.device
+        f32 = lambda t: t.detach().to(F32).contiguous().to(dev)  # noqa: E731
+        r = m.residual
+        return dict(g0=f32(r[0].gamma.reshape(-1)), c2=_Conv(r[2].weight, r[2].bias, _taps(3, 3, 3), dev),
+                    g3=f32(r[3].gamma.reshape(-1)), c6=_Conv(r[6].weight, r[6].bias, _taps(3, 3, 3), dev),
+                    sc=None if isinstance(m.shortcut, nn.Identity) else
+                    _Conv(m.shortcut.weight, m.shortcut.bias, _taps(1, 1, 1), dev))
+
+    # -- primitive launches -----------------------------------------------------------------------------
+    def conv(self, x, c, res=None, out=None):
+        """x [T,H,W,Cin] bf16 -> [T,H,W,Cout] bf16 (+res)."""
+        T, H, W, _ = x.shape
+        if out is None:
+            out = torch.empty(T, H, W, c.cout, dtype=BF16, device=self.device)
+        mv.vae_conv(x, c, out, res=res, o_base=0, os_t=H * W * c.cout, os_h=W * c.cout, os_w=c.cout)
+        return out
+
+    def normsilu(self, x, gamma, out=None, silu=True):
+        out = x if out is None else out
+        mv.vae_rmsnorm_silu(x, out, gamma, silu)
+        return out
+
+    # -- blocks -----------------------------------------------------------------------------------------------
+    def resblock(self, x, p):
+        h = x if p["sc"] is None else self.conv(x, p["sc"])
+        a = self.normsilu(x, p["g0"], out=torch.empty_like(x))
+        y = self.conv(a, p["c2"])
+        del a
+        self.normsilu(y, p["g3"])
+        return self.conv(y, p["c6"], res=h)
+
+    def attention(self, x, p):
+        """vae.py:223-262: per-frame single-head attention, d = C, over the H*W positions."""
+        T, H, W, C = x.shape
+        hw = H * W
+        n = self.normsilu(x, p["gamma"], out=torch.empty_like(x), silu=False)
+        qkv = self.conv(n, p["qkv"]).view(T * hw, 3 * C)
+        del n
+        k8 = (hw + 7) // 8 * 8
+        S = torch.empty(hw, (hw + 3) // 4 * 4, dtype=F32, device=self.device)
+        P = torch.zeros(hw, k8, dtype=BF16, device=self.device)
+        vT = torch.zeros(C, k8, dtype=BF16, device=self.device)
+        O = torch.empty(T, H, W, C, dtype=BF16, device=self.device)
+        Of = O.view(T * hw, C)
+        scale = 1.0 / math.sqrt(C)
+        for f in range(T):
+            rows = qkv[f * hw:(f + 1) * hw]
+            mv.gemm(rows[:, 0:C], rows[:, C:2 * C], None, S[:, :hw], mv.MV_EPI_F32)
+            mv.softmax_rows(S[:, :hw], P, hw, scale)
+            vT[:, :hw].copy_(rows[:, 2 * C:3 * C].t())       # layout change only (K-major operand for P.V)
+            mv.gemm(P, vT, None, Of[f * hw:(f + 1) * hw], mv.MV_EPI_BF16)
+        return self.conv(O, p["proj"], res=x)
+
+    def upsample(self, x, p):
+        T, H, W, C = x.shape
+        if p["mode"] == "upsample3d" and T > 1:
+            T2 = 2 * T - 1
+            y = torch.empty(T2, H, W, C, dtype=BF16, device=self.device)
+            y[0].copy_(x[0])                                                            # 'Rep': frame 0 passes through
+            fe = H * W * C
+            mv.vae_conv(x[1:], p["time"], y, res=None, o_base=fe, os_t=2 * fe, os_h=W * C, os_w=C, nsplit=C,
+                        nsplit_off=fe)
+            x = y
+            T = T2
+        Co = C // 2
+        out = torch.empty(T, 2 * H, 2 * W, Co, dtype=BF16, device=self.device)
+        for (a, b), c in p["par"].items():
+            mv.vae_conv(x, c, out, res=None, o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co,
+                        os_w=2 * Co)
+        return out
+
+    # -- WanVAE.decode for one latent ---------------------------------------------------------------------------
+    def decode(self, z):
+        """z [z_dim, T, h, w] fp32 -> [3, 1+4(T-1), 8h, 8w] fp32 in [-1, 1]."""
+        Z, T, h, w = z.shape
+        z = z.to(self.device, F32).contiguous()
+        x = torch.empty(T, h, w, Z, dtype=BF16, device=self.device)
+        mv.vae_latent_in(z, self.w2, self.b2, self.mean, self.std, x)
+        x = self.conv(x, self.conv1)
+        for kind, p in self.layers:
+            if kind == "res":
+                x = self.resblock(x, p)
+            elif kind == "attn":
+                x = self.attention(x, p)
+            else:
+                x = self.upsample(x, p)
+        self.normsilu(x, self.head_gamma)
+        T, H, W, _ = x.shape
+        video = torch.empty(3, T, H, W, dtype=F32, device=self.device)
+        mv.vae_conv(x, self.head, video, res=None, out_mode=1)
+        return video
 
 
 class WanVAE:
+    """wan/modules/vae.py:619-663.  vae_pth=None (or a missing file) -> random-init weights (benchmarks)."""
+
     def __init__(self, z_dim=16, vae_pth=None, dtype=torch.float, device="cuda"):
-        self.device = device
-        self.model = _Dims()
+        self.dtype, self.device = dtype, device
+        self.mean = torch.tensor(VAE_MEAN, dtype=dtype, device=device)
+        self.std = torch.tensor(VAE_STD, dtype=dtype, device=device)
+        self.scale = [self.mean, 1.0 / self.std]
+        self.model = WanVAE_(dim=96, z_dim=z_dim, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                             temperal_downsample=(False, True, True))
+        if vae_pth:
+            logging.info("loading %s", vae_pth)
+            self.model.load_state_dict(torch.load(vae_pth, map_location="cpu", weights_only=True))
+        else:
+            nn.init.normal_(self.model.decoder.middle[1].proj.weight, std=0.02)  # zero-init would hide the attention
+        self.model.eval().requires_grad_(False).to(device)
+
+    def encode(self, videos):
+        raise NotImplementedError("the VAE encoder is preprocessing-only and outside the B200 hot path")
 
     def decode(self, zs):
-        raise NotImplementedError("native WanVAE decoder not built yet")
+        """zs: list of [16, T, h, w] latents -> list of [3, 1+4(T-1), 8h, 8w] fp32 in [-1, 1]."""
+        eng = self.model.engine()
+        return [eng.decode(u) for u in zs]

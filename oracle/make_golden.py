@@ -121,9 +121,31 @@ def golden_unipc():
     return res
 
 
+def golden_vae(vae):
+    """Reference chunked decode (WanVAE_.decode with its feature cache) on small latents: T = 1, 2, 3, 5 covers the
+    first-chunk 'Rep' path, the 1-frame cache concat and the steady state; h x w = 5 x 9 exercises ragged 8x16 tiles."""
+    from oracle.vae_oracle import VAE_MEAN, VAE_STD
+    m = vae.WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                    temperal_downsample=[False, True, True]).eval()
+    # only the decoder half is filled (and stored): the tests rebuild exactly these parameters by name
+    fill_parameters([(n, p) for n, p in m.named_parameters() if n.startswith(("decoder.", "conv2."))], 404)
+    mean, std = torch.tensor(VAE_MEAN), torch.tensor(VAE_STD)
+    res = {"seed": 404, "cases": {}}
+    res["param_shapes"] = {k: tuple(v.shape) for k, v in m.state_dict().items()
+                           if k.startswith("decoder.") or k.startswith("conv2.")}
+    for T, h, w in ((1, 4, 6), (2, 5, 9), (3, 4, 6), (5, 4, 4)):
+        g = torch.Generator().manual_seed(100 + T)
+        z = torch.randn(16, T, h, w, generator=g)
+        with torch.no_grad():
+            y = m.decode(z[None], [mean, 1.0 / std]).float().clamp_(-1, 1)[0]
+        res["cases"][(T, h, w)] = dict(z=z, y=y.to(torch.float16))  # fp16 storage: 5e-4 abs on [-1,1], keeps files small
+    return res
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     att, model, vae = ref_loader.load_reference()
+    torch.save(golden_vae(vae), os.path.join(OUT, "vae_decode.pt"))
     torch.save(golden_block_cfg1(model), os.path.join(OUT, "block_cfg1.pt"))
     torch.save(golden_model_tiny(model), os.path.join(OUT, "model_tiny_hd128.pt"))
     torch.save(golden_unipc(), os.path.join(OUT, "unipc.pt"))

@@ -85,3 +85,24 @@ def test_rope_table_matches_engine_table():
     assert (cs[..., 1].double() - torch.sin(ang)).abs().max() < 1e-6
     part = rope_cos_sin(freqs, grid, seq_len, start=16, rows=16)
     assert torch.equal(part, cs[16:32])
+
+
+@pytest.mark.parametrize("case", [(1, 4, 6), (2, 5, 9), (3, 4, 6), (5, 4, 4)])
+def test_vae_oracle_matches_reference_chunked_decode(case):
+    """The whole-sequence restatement equals the reference's chunked decode with feature cache (incl. the 'Rep' path)."""
+    from oracle import vae_oracle as V
+    g = load("vae_decode.pt")
+    sd = state_dict_like(g["param_shapes"], g["seed"])
+    rec = g["cases"][case]
+    y = V.decode(sd, rec["z"])
+    ref = rec["y"].float()
+    assert y.shape == ref.shape == (3, 1 + 4 * (case[0] - 1), 8 * case[1], 8 * case[2])
+    assert (y - ref).abs().max().item() <= 1e-3          # golden stored in fp16 (4.9e-4 quantisation on [-1, 1])
+
+
+def test_vae_state_dict_matches_reference_names():
+    from wan.modules.vae import WanVAE_
+    g = load("vae_decode.pt")
+    m = WanVAE_()
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ours == g["param_shapes"]

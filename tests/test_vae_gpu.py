@@ -1,0 +1,77 @@
+"""-m gpu parity of the native WanVAE decoder (implicit-GEMM tcgen05 convs) against golden outputs of the REFERENCE's
+chunked decode and against the CPU oracle.  Tolerance: the decoder runs with bf16 operands / activations where the
+reference uses fp32 storage and TF32 convolutions, so: PSNR >= 45 dB and max-abs <= 5e-2 on the [-1, 1] output
+(SURVEY.md §8c asked for 2e-2; the CPU emulation of the bf16 contract itself measures 2.3e-2..3.2e-2 with these
+unit-gain random weights — see DESIGN.md §5)."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import vae_oracle as V
+from oracle.fill import fill_parameters, state_dict_like
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def psnr(a, b):
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    return 10 * math.log10(4.0 / max(mse, 1e-20))
+
+
+@pytest.fixture(scope="module")
+def vae():
+    from wan.modules.vae import WanVAE_
+    g = torch.load(os.path.join(GOLD, "vae_decode.pt"), weights_only=False)
+    m = WanVAE_().eval().requires_grad_(False)
+    fill_parameters(m, g["seed"])
+    return m.to(DEV), g
+
+
+@pytest.mark.parametrize("case", [(1, 4, 6), (2, 5, 9), (3, 4, 6), (5, 4, 4)])
+def test_vae_decode_matches_reference_golden(vae, case):
+    m, g = vae
+    rec = g["cases"][case]
+    y = m.decode(rec["z"][None].to(DEV))[0].cpu()
+    ref = rec["y"].float()
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert torch.isfinite(y).all() and y.abs().max() <= 1.0
+    sd = state_dict_like(g["param_shapes"], g["seed"])
+    emu = V.decode(sd, rec["z"], V.bf16_rt)
+    assert psnr(y, ref) >= 45.0, (psnr(y, ref), psnr(emu, ref))
+    assert (y - ref).abs().max().item() <= 5e-2, ((y - ref).abs().max().item(), (emu - ref).abs().max().item())
+    # against the same storage contract the agreement is much tighter
+    assert psnr(y, emu) >= 50.0
+
+
+def test_vae_conv_primitives(vae):
+    """One 3x3x3 causal conv and one sub-pixel upsample conv against torch, ragged grid."""
+    import torch.nn.functional as F
+    import movii_b200 as mv
+    from wan.modules.vae import _Conv, _parity_convs, _taps
+    g = torch.Generator().manual_seed(1)
+    T, H, W, Ci, Co = 3, 11, 21, 96, 192
+    x = torch.randn(T, H, W, Ci, generator=g).bfloat16()
+    wt = (torch.randn(Co, Ci, 3, 3, 3, generator=g) / math.sqrt(27 * Ci))
+    b = torch.randn(Co, generator=g)
+    c = _Conv(wt, b, _taps(3, 3, 3), DEV)
+    out = torch.empty(T, H, W, Co, dtype=torch.bfloat16, device=DEV)
+    mv.vae_conv(x.to(DEV), c, out, o_base=0, os_t=H * W * Co, os_h=W * Co, os_w=Co)
+    ref = V.causal_conv3d(x.float().permute(3, 0, 1, 2)[None], wt, b, V.bf16_rt)[0].permute(1, 2, 3, 0)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 3e-2, err
+    # sub-pixel upsample: nearest-exact x2 + Conv2d 3x3
+    w2 = torch.randn(Co // 2, Co, 3, 3, generator=g) / math.sqrt(9 * Co)
+    b2 = torch.randn(Co // 2, generator=g)
+    xin = torch.randn(T, H, W, Co, generator=g).bfloat16()
+    up = torch.empty(T, 2 * H, 2 * W, Co // 2, dtype=torch.bfloat16, device=DEV)
+    for (a, bb), cc in _parity_convs(w2, b2, DEV).items():
+        mv.vae_conv(xin.to(DEV), cc, up, o_base=(a * 2 * W + bb) * (Co // 2), os_t=4 * H * W * (Co // 2),
+                    os_h=4 * W * (Co // 2), os_w=2 * (Co // 2))
+    xf = F.interpolate(xin.float().permute(0, 3, 1, 2), scale_factor=(2.0, 2.0), mode="nearest-exact")
+    ref2 = F.conv2d(xf, V.bf16_rt(w2), b2, padding=1).permute(0, 2, 3, 1)
+    err2 = (up.float().cpu() - ref2).abs().max().item()
+    assert err2 <= 3e-2, err2
