@@ -22,7 +22,7 @@ namespace mv {
 constexpr int kConvBM = 128;
 constexpr int kConvTW = 16;   // tile width  (w)
 constexpr int kConvTH = 8;    // tile height (h)
-constexpr int kConvStages = 5;
+constexpr int kConvStages = 4;
 constexpr int kConvThreads = 192;
 constexpr int kConvMaxTaps = 27;
 constexpr uint32_t kConvABytesMax = kConvBM * 64 * 2;   // 16 KB

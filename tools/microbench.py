@@ -98,3 +98,7 @@ if __name__ == "__main__":
             bench_attn(L, H, Lk)
     if "rowops" in which:
         bench_rowops()
+    if "attn_one" in which:      # single launch for an ncu --set full capture
+        bench_attn(75600, 5, None)
+    if "gemm_one" in which:
+        bench_gemm(75600, 5120, 5120, 2)

@@ -1,0 +1,54 @@
+"""Multi-GPU check of the Ulysses path (run under torchrun, one rank per GPU): the sequence-parallel forward of a
+small WanModel must equal the single-GPU forward of the same model (SP oracle = P=1 result,
+rel-L2 <= 2e-3).  Prints PASS/FAIL on rank 0 and exits non-zero on failure."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "moviigen1.1_b200"))
+
+
+def main():
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import types
+    from xfuser.core.distributed import init_distributed_environment, initialize_model_parallel
+    from oracle.fill import fill_parameters
+    from wan.distributed.xdit_context_parallel import usp_dit_forward
+    from wan.modules.model import WanModel
+    init_distributed_environment(rank=rank, world_size=world)
+    initialize_model_parallel(sequence_parallel_degree=world, ring_degree=1, ulysses_degree=world)
+    heads = 8
+    cfg = dict(model_type="t2v", patch_size=(1, 2, 2), text_len=32, in_dim=16, dim=128 * heads, ffn_dim=2048,
+               freq_dim=64, text_dim=128, out_dim=16, num_heads=heads, num_layers=3, eps=1e-6)
+    m = WanModel(**cfg).eval().requires_grad_(False)
+    fill_parameters(m, 77)
+    m.to(dev)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(16, 3, 16, 32, generator=g).to(dev)      # grid 3 x 8 x 16 = 384 tokens
+    ctx = torch.randn(20, 128, generator=g).to(dev)
+    t = torch.tensor([500], device=dev)
+    seq_len = 384
+    ok = True
+    y1 = m([x], t, [ctx], seq_len)[0]
+    m.forward = types.MethodType(usp_dit_forward, m)
+    ysp = m([x], t, [ctx], seq_len)[0]
+    rel = ((ysp - y1).double().norm() / y1.double().norm()).item()
+    ok = ok and rel <= 2e-3 and bool(torch.isfinite(ysp).all())
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    if rank == 0:
+        print("SP%d vs SP1 rel-L2 = %.3e -> %s" % (world, rel, "PASS" if flag.item() == 0 else "FAIL"), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

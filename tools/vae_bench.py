@@ -1,0 +1,50 @@
+"""WanVAE decode benchmark (BASELINE.json configs[3]): frames/s of WanVAE.decode on a synthetic latent, one B200.
+Prints one JSON line.  VAE FLOPs/bytes per SURVEY.md §8d (1080P: 1116.5 TF, 720P: 639.2 TF)."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "moviigen1.1_b200"))
+import movii_b200 as mv  # noqa: E402
+from wan.modules.vae import WanVAE  # noqa: E402
+
+SHAPES = {"1080p": (21, 104, 240, 1116.5), "720p": (21, 90, 160, 639.2), "480p": (21, 60, 104, None),
+          "small": (5, 32, 32, None)}
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "1080p"
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    T, h, w, tf = SHAPES[which]
+    mv.device_check()
+    torch.manual_seed(3)
+    vae = WanVAE(vae_pth=None, device="cuda")
+    z = torch.randn(16, T, h, w, device="cuda")
+    out = vae.decode([z])[0]  # warm-up (also builds the engine)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        l0 = mv.LAUNCHES
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = vae.decode([z])[0]
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+        launches = mv.LAUNCHES - l0
+    ms = sorted(ts)[len(ts) // 2]
+    frames = out.shape[1]
+    rec = dict(metric="vae_decode_fps", workload=which, latent=[16, T, h, w], out=list(out.shape), ms=round(ms, 2),
+               value=round(frames / ms * 1e3, 2), unit="frames/s", gpu_launches=launches,
+               finite=bool(torch.isfinite(out).all()), peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 1))
+    if tf:
+        rec["tflops"] = round(tf / ms * 1e3, 1)
+    print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    main()
