@@ -1,18 +1,24 @@
 // Flash-attention forward for the DiT (head_dim 128, bf16, non-causal) on tcgen05 / TMEM / TMA.
 //
-// One CTA = one head x 256 query rows (two 128-row Q tiles that ping-pong on the tensor pipe):
-//   warp 0       TMA producer: Q (once), then K_0, V_0, K_1, V_1, ... through a 4 x 32 KB ring
-//   warp 1       MMA issuer (one thread): S_w = Q_w K_j^T (SS), O_w += P_w V_j (A = P from TMEM, B = V
-//                MN-major from smem); TMEM: S0|S1|O0|O1 = 4 x 128 fp32 columns; P_w (bf16) aliases S_w
-//   warps 4-7    softmax warpgroup for Q tile 0: one thread per query row, S from TMEM, online softmax
+// One CTA = one head x 256 query rows = two 128-row Q tiles (w = 0, 1).  Keys are consumed in steps of 64.
+//   warp 0       TMA producer: Q (once), then K_0, K_1, V_0, K_2, V_1, ... through an 8 x 16 KB ring
+//   warp 1       MMA issuer (one thread):  S_w[b] = Q_w K_j^T  (SS, M128 N64 K16 x 8)
+//                                          O_w   += P_w[b] V_j (A = P from TMEM, B = V MN-major smem, N128 K16 x 4)
+//   warps 4-7    softmax warpgroup for Q tile 0: one thread per query row
 //   warps 8-11   same for Q tile 1
-// The O accumulator is rescaled lazily (only when a row max grew by more than 2^8, FA4-style), by the
-// softmax warpgroup itself, after waiting for the previous P.V of its tile; the final 1/l scaling and the
-// bf16 store are done by the same threads.
+// TMEM (512 columns): S_0[0] S_0[1] S_1[0] S_1[1] (4 x 64 fp32 columns) | O_0 | O_1 (2 x 128).  P (bf16, 32 columns)
+// overwrites the S buffer it came from.  S is DOUBLE-BUFFERED per Q tile: Q K_{j+2}^T is issued right after
+// P V_j, i.e. two steps ahead, so the softmax warpgroups never wait for the tensor pipe and the tensor pipe only
+// ever waits for P — the score GEMM is off the softmax -> PV critical path (v1 of this kernel had a single S
+// buffer per tile and paid softmax + PV + QK in series).
+// Online softmax in fp32 with exp2; the O accumulator is rescaled lazily (only when a row max grew by more than
+// 2^8, FA4-style) by the softmax warpgroup itself after waiting for the previous P.V; final 1/l scaling and bf16
+// store by the same threads.
 //
 // Replaces flash_attn.flash_attn_varlen_func (FA2 mma.sync kernels) called from
 // wan/modules/attention.py:113-127 for self-attention (model.py:146-151) and cross-attention (:176).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -21,12 +27,15 @@ namespace mv {
 
 constexpr int kD = 128;             // head dim
 constexpr int kBQ = 128;            // rows per Q tile
-constexpr int kBKV = 128;           // keys per KV tile
-constexpr int kKVStages = 4;        // ring of 32 KB tiles (K and V alternate)
+constexpr int kBKV = 64;            // keys per step
+constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
-constexpr uint32_t kTileBytes = kBQ * kD * 2;       // 32 KB
-constexpr uint32_t kHalfBytes = kTileBytes / 2;     // one [128 x 64] 128B-swizzled sub-tile
-constexpr uint32_t kAttnSmem = 2 * kTileBytes + kKVStages * kTileBytes + 1024 + 256;
+constexpr int kDefaultEmu = 0;
+constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
+constexpr uint32_t kQHalfBytes = kQTileBytes / 2;    // [128 x 64] 128B-swizzled sub-tile
+constexpr uint32_t kKVTileBytes = kBKV * kD * 2;     // 16 KB
+constexpr uint32_t kKVHalfBytes = kKVTileBytes / 2;  // [64 x 64] sub-tile
+constexpr uint32_t kAttnSmem = 2 * kQTileBytes + kKVStages * kKVTileBytes + 1024 + 512;
 
 struct AttnParams {
   __nv_bfloat16* o;
@@ -35,20 +44,40 @@ struct AttnParams {
   float scale_log2;
 };
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// 2^x on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error 1.6e-4 —
+// far below the bf16 rounding of P).  Used for a fraction of the exponentials so that the MUFU pipe
+// (16 ex2/clk/SM, exactly as many cycles per tile as the tensor pipe needs) is not the co-bottleneck (FA4).
+__device__ __forceinline__ float exp2_emu(float x) {
+  x = fmaxf(x, -125.f);
+  const float xr = x + 12582912.f;            // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float f = x - (xr - 12582912.f);      // fractional part in [-0.5, 0.5]
+  float pz = fmaf(0.05360212177038193f, f, 0.24237291514873505f);
+  pz = fmaf(pz, f, 0.6935023665428162f);
+  pz = fmaf(pz, f, 0.9999481439590454f);
+  return __int_as_float(__float_as_int(pz) + (__float_as_int(xr) << 23));
+}
+
+template <int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                       // 2 tiles
-  uint8_t* sKV = smem + 2 * kTileBytes;     // ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kKVStages) * kTileBytes);
-  uint64_t* q_full = bars;                  // 1
-  uint64_t* kv_full = bars + 1;             // kKVStages
-  uint64_t* kv_empty = kv_full + kKVStages; // kKVStages
-  uint64_t* s_full = kv_empty + kKVStages;  // 2
-  uint64_t* p_full = s_full + 2;            // 2
-  uint64_t* o_done = p_full + 2;            // 2
+  uint8_t* sQ = smem;                        // 2 tiles
+  uint8_t* sKV = smem + 2 * kQTileBytes;     // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTileBytes + kKVStages * kKVTileBytes);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* kv_full = bars + 1;              // kKVStages
+  uint64_t* kv_empty = kv_full + kKVStages;  // kKVStages
+  uint64_t* s_full = kv_empty + kKVStages;   // [w][b] -> 4
+  uint64_t* p_full = s_full + 4;             // [w][b] -> 4
+  uint64_t* o_done = p_full + 4;             // [w]    -> 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -66,11 +95,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrive per softmax warp
-      mbar_init(&o_done[i], 1);
     }
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -80,28 +110,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0 && lane == 0) {
       // ------------------------------ TMA producer ------------------------------
-      mbar_expect_tx(q_full, 2 * kTileBytes);
+      mbar_expect_tx(q_full, 2 * kQTileBytes);
 #pragma unroll
       for (int w = 0; w < 2; ++w)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-          tma_load_3d(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
+          tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
       int stage = 0;
       uint32_t phase = 0;
-      for (int i = 0; i < 2 * n_kv; ++i) {
-        const int j = i >> 1;
-        const CUtensorMap* tm = (i & 1) ? &tmV : &tmK;
+      auto load_tile = [&](const CUtensorMap* tm, int j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_expect_tx(&kv_full[stage], kTileBytes);
-        tma_load_3d(sKV + stage * kTileBytes, tm, &kv_full[stage], 0, head, j * kBKV);
-        tma_load_3d(sKV + stage * kTileBytes + kHalfBytes, tm, &kv_full[stage], 64, head, j * kBKV);
+        mbar_expect_tx(&kv_full[stage], kKVTileBytes);
+        tma_load_3d(sKV + stage * kKVTileBytes, tm, &kv_full[stage], 0, head, j * kBKV);
+        tma_load_3d(sKV + stage * kKVTileBytes + kKVHalfBytes, tm, &kv_full[stage], 64, head, j * kBKV);
         if (++stage == kKVStages) {
           stage = 0;
           phase ^= 1;
         }
+      };
+      load_tile(&tmK, 0);
+      if (n_kv > 1) load_tile(&tmK, 1);
+      for (int j = 0; j < n_kv; ++j) {
+        load_tile(&tmV, j);
+        if (j + 2 < n_kv) load_tile(&tmK, j + 2);
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------ MMA issuer --------------------------------
@@ -109,23 +143,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
       const uint32_t sQ_addr = smem_u32(sQ);
       const uint32_t sKV_addr = smem_u32(sKV);
-      auto issue_qk = [&](int w, int st) {
-        const uint32_t d_tmem = tmem_base + w * 128;
+      auto issue_qk = [&](int w, int st, int b) {
+        const uint32_t d_tmem = tmem_base + (w * 2 + b) * 64;
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) {
-          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-          const uint64_t adesc = make_desc_kmajor_sw128(sQ_addr + w * kTileBytes + off);
-          const uint64_t bdesc = make_desc_kmajor_sw128(sKV_addr + st * kTileBytes + off);
+          const uint64_t adesc = make_desc_kmajor_sw128(sQ_addr + w * kQTileBytes + (k >> 2) * kQHalfBytes + (k & 3) * 32);
+          const uint64_t bdesc = make_desc_kmajor_sw128(sKV_addr + st * kKVTileBytes + (k >> 2) * kKVHalfBytes + (k & 3) * 32);
           umma_ss(d_tmem, adesc, bdesc, idesc_qk, k != 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int w, int st, uint32_t acc) {
+      auto issue_pv = [&](int w, int st, int b, uint32_t acc) {
         const uint32_t d_tmem = tmem_base + 256 + w * 128;
-        const uint32_t a_tmem = tmem_base + w * 128;  // P_w: 64 columns of packed bf16 pairs
+        const uint32_t a_tmem = tmem_base + (w * 2 + b) * 64;  // P: 32 columns of packed bf16 pairs
 #pragma unroll
         for (int k = 0; k < kBKV / 16; ++k) {
-          // 16 keys = 2 eight-row groups of 1024 B; the two 64-wide d halves are kHalfBytes apart
-          const uint64_t bdesc = make_desc_mnmajor_sw128(sKV_addr + st * kTileBytes + k * 2048, kHalfBytes);
+          // 16 keys = 2 eight-row groups of 1024 B; the two 64-wide d halves are kKVHalfBytes apart
+          const uint64_t bdesc = make_desc_mnmajor_sw128(sKV_addr + st * kKVTileBytes + k * 2048, kKVHalfBytes);
           umma_ts(d_tmem, a_tmem + k * 8, bdesc, idesc_pv, (acc | k) != 0 ? 1u : 0u);
         }
       };
@@ -138,84 +171,85 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[stage], phase);
-      tc_fence_after();
-      issue_qk(0, stage);
-      umma_commit(&s_full[0]);
-      issue_qk(1, stage);
-      umma_commit(&s_full[1]);
-      umma_commit(&kv_empty[stage]);
-      advance();
+      // prologue: scores of steps 0 and 1
+      for (int j = 0; j < 2 && j < n_kv; ++j) {
+        mbar_wait(&kv_full[stage], phase);
+        tc_fence_after();
+        issue_qk(0, stage, j);
+        umma_commit(&s_full[0 * 2 + j]);
+        issue_qk(1, stage, j);
+        umma_commit(&s_full[1 * 2 + j]);
+        umma_commit(&kv_empty[stage]);
+        advance();
+      }
       for (int j = 0; j < n_kv; ++j) {
+        const int b = j & 1;
+        const uint32_t par = (j >> 1) & 1;
         const int vstage = stage;
         const uint32_t vphase = phase;
         advance();
-        const bool more = (j + 1 < n_kv);
+        const bool more = (j + 2 < n_kv);
         const int kstage = stage;
         const uint32_t kphase = phase;
         if (more) advance();
-        const uint32_t par = j & 1;
         mbar_wait(&kv_full[vstage], vphase);
-        mbar_wait(&p_full[0], par);
-        tc_fence_after();
-        issue_pv(0, vstage, j > 0 ? 1u : 0u);
-        umma_commit(&o_done[0]);
-        if (more) {
-          mbar_wait(&kv_full[kstage], kphase);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&p_full[w * 2 + b], par);
           tc_fence_after();
-          issue_qk(0, kstage);
-          umma_commit(&s_full[0]);
+          issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
+          umma_commit(&o_done[w]);
+          if (more) {
+            if (w == 0) {
+              mbar_wait(&kv_full[kstage], kphase);
+              tc_fence_after();
+            }
+            issue_qk(w, kstage, b);
+            umma_commit(&s_full[w * 2 + b]);
+          }
         }
-        mbar_wait(&p_full[1], par);
-        tc_fence_after();
-        issue_pv(1, vstage, j > 0 ? 1u : 0u);
-        umma_commit(&o_done[1]);
         umma_commit(&kv_empty[vstage]);
-        if (more) {
-          issue_qk(1, kstage);
-          umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[kstage]);
-        }
+        if (more) umma_commit(&kv_empty[kstage]);
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------ softmax warpgroups ------------------------
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + wg * 128;
+    const uint32_t tS0 = tmem_base + lane_base + wg * 128;        // S_w[b] = tS0 + b * 64
     const uint32_t tO = tmem_base + lane_base + 256 + wg * 128;
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[wg], j & 1);
+      const int b = j & 1;
+      const uint32_t tS = tS0 + b * 64;
+      mbar_wait(&s_full[wg * 2 + b], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t s[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, s[c]);
+      uint32_t s[2][32];
+      tmem_ld_x32(tS, s[0]);
+      tmem_ld_x32(tS + 32, s[1]);
       tc_wait_ld();
       const int valid = p.Lk - j * kBKV;
       if (valid < kBKV) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[c][i + 0]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+          mx0 = fmax3(mx0, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
         }
-      const float m_new = fmaxf(fmaxf(m_run, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+      const float m_new = fmax3(m_run, mx0, mx1);
       if (j == 0) {
         m_run = m_new;
       } else {
@@ -239,25 +273,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       const float neg_m = -m_run * sl2;
-      float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[2][32];
+      const float2 sc2 = make_float2(sl2, sl2);
+      const float2 nm2 = make_float2(neg_m, neg_m);
+      float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c][i]), sl2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[c][i + 1]), sl2, neg_m));
-          sum0 += p0;
-          sum1 += p1;
-          pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+        for (int i = 0; i < 32; i += 4) {
+          const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+          const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+          float2 e01, e23;
+          e01.x = fast_exp2(x01.x);
+          e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
+          e23.x = fast_exp2(x23.x);
+          e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
+          sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
+          pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+          pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
         }
-      l_run += sum0 + sum1;
-      tmem_st_x32(tS, pk[0]);
-      tmem_st_x32(tS + 32, pk[1]);
+      l_run += sum2.x + sum2.y;
+      tmem_st_x32(tS, pk);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[wg]);
+      if (lane == 0) mbar_arrive(&p_full[wg * 2 + b]);
     }
 
     // ------------------------------ final epilogue ----------------------------
@@ -311,15 +351,15 @@ extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64
   MV_REQUIRE(H <= 65535, "mv_attention_fwd: too many heads");
 
   CUtensorMap tmQ, tmK, tmV;
-  auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int L) {
+  auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int L, int box_rows) {
     uint64_t dims[3] = {static_cast<uint64_t>(kD), static_cast<uint64_t>(H), static_cast<uint64_t>(L)};
     uint64_t str[3] = {2, static_cast<uint64_t>(kD) * 2, static_cast<uint64_t>(ld) * 2};
-    uint32_t box[3] = {64, 1, static_cast<uint32_t>(kBQ)};
+    uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
     return make_tmap_bf16(tm, base, 3, dims, str, box, true);
   };
-  if ((rc = mk(&tmQ, q, ldq, Lq)) != MV_OK) return rc;
-  if ((rc = mk(&tmK, k, ldk, Lk)) != MV_OK) return rc;
-  if ((rc = mk(&tmV, v, ldv, Lk)) != MV_OK) return rc;
+  if ((rc = mk(&tmQ, q, ldq, Lq, kBQ)) != MV_OK) return rc;
+  if ((rc = mk(&tmK, k, ldk, Lk, kBKV)) != MV_OK) return rc;
+  if ((rc = mk(&tmV, v, ldv, Lk, kBKV)) != MV_OK) return rc;
 
   AttnParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
@@ -329,14 +369,23 @@ extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64
   p.n_kv = (Lk + kBKV - 1) / kBKV;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // fraction of exponentials evaluated on the FMA pipe: 0 = none, 1 = 1/4, 2 = 1/2 (MV_ATTN_EMU overrides)
+  static int emu = -1;
+  if (emu < 0) {
+    const char* e = getenv("MV_ATTN_EMU");
+    emu = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : kDefaultEmu;
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem)));
-    attr_set = true;
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
-  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (emu == 2) attention_fwd_kernel<2><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
+  else if (emu == 1) attention_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
+  else attention_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   MV_CHECK_LAUNCH("attention_fwd_kernel");
   return MV_OK;
 }

@@ -24,7 +24,8 @@ constexpr int kGemmThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 2;  // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kGemmSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kEpiStageBytes = 4 * 4096;  // one 32x32 fp32 transpose buffer per epilogue warp
+constexpr uint32_t kGemmSmem = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmParams {
   const float* bias;
@@ -54,7 +55,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* sEpi = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kEpiStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
@@ -144,16 +146,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
+    // TMEM -> registers (one accumulator row per thread) -> per-warp smem transpose -> global, so that every
+    // global access of a warp covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* stg = sEpi + quad * 4096;  // 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
     int as = 0;
     uint32_t aphase = 0;
+    const int rr0 = lane >> 3;   // row inside a 4-row group
+    const int cc = lane & 7;     // 16-byte column chunk = 4 fp32 accumulator columns
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(p, tile, m_blk, n_blk);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m_blk * BM + quad * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -162,71 +168,76 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         tmem_ld_x32(taddr + c * 32, r);
         tc_wait_ld();
-        if (row_ok) {
-          float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float b = 0.f;
-            if (p.bias != nullptr && col0 + i < p.N) b = __ldg(p.bias + col0 + i);
-            v[i] = __uint_as_float(r[i]) + b;
-            if constexpr (EPI != MV_EPI_F32) v[i] = bf16_round(v[i]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        const int col = col0 + cc * 4;
+        const bool col_full = (col + 4 <= p.N);
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        float g4[4] = {1.f, 1.f, 1.f, 1.f};
+        if (col_full) {
+          if (p.bias != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
           }
-          const bool full_chunk = (col0 + 32 <= p.N);
-          if constexpr (EPI == MV_EPI_BF16 || EPI == MV_EPI_BF16_GELU) {
+          if (EPI == MV_EPI_RESID_F32 && p.gate != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.gate + col));
+            g4[0] = t.x; g4[1] = t.y; g4[2] = t.z; g4[3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i < p.N) {
+              if (p.bias != nullptr) b4[i] = __ldg(p.bias + col + i);
+              if (EPI == MV_EPI_RESID_F32 && p.gate != nullptr) g4[i] = __ldg(p.gate + col + i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = rr0 + 4 * k;
+          const int row = row_base + rr;
+          const uint4 a = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          if (row < p.M && col < p.N) {
+            float v[4] = {__uint_as_float(a.x) + b4[0], __uint_as_float(a.y) + b4[1], __uint_as_float(a.z) + b4[2],
+                          __uint_as_float(a.w) + b4[3]};
+            if constexpr (EPI != MV_EPI_F32) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[i] = bf16_round(v[i]);
+            }
             if constexpr (EPI == MV_EPI_BF16_GELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+              for (int i = 0; i < 4; ++i) v[i] = gelu_tanh(v[i]);
             }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
-            if (full_chunk) {
-              uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 w;
-                w.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-                w.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-                w.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-                w.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-                o4[i] = w;
+            if constexpr (EPI == MV_EPI_BF16 || EPI == MV_EPI_BF16_GELU) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo + col;
+              if (col_full) {
+                *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+              } else {
+                for (int i = 0; i < 4 && col + i < p.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
               }
             } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
-            if (full_chunk) {
-              float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(row) * p.ldo + col;
+              if (col_full) {
                 float4 w;
                 if constexpr (EPI == MV_EPI_RESID_F32) {
-                  float4 x = o4[i];
-                  float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
-                  if (p.gate != nullptr) {
-                    float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + col0) + i);
-                    g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
-                  }
-                  w.x = x.x + v[4 * i + 0] * g0;
-                  w.y = x.y + v[4 * i + 1] * g1;
-                  w.z = x.z + v[4 * i + 2] * g2;
-                  w.w = x.w + v[4 * i + 3] * g3;
+                  const float4 x = *reinterpret_cast<const float4*>(o);
+                  w.x = x.x + v[0] * g4[0]; w.y = x.y + v[1] * g4[1]; w.z = x.z + v[2] * g4[2]; w.w = x.w + v[3] * g4[3];
                 } else {
-                  w.x = v[4 * i + 0]; w.y = v[4 * i + 1]; w.z = v[4 * i + 2]; w.w = v[4 * i + 3];
+                  w.x = v[0]; w.y = v[1]; w.z = v[2]; w.w = v[3];
                 }
-                o4[i] = w;
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
-                if constexpr (EPI == MV_EPI_RESID_F32) {
-                  float g = p.gate != nullptr ? __ldg(p.gate + col0 + i) : 1.f;
-                  o[i] = o[i] + v[i] * g;
-                } else {
-                  o[i] = v[i];
+                *reinterpret_cast<float4*>(o) = w;
+              } else {
+                for (int i = 0; i < 4 && col + i < p.N; ++i) {
+                  if constexpr (EPI == MV_EPI_RESID_F32) o[i] = o[i] + v[i] * g4[i];
+                  else o[i] = v[i];
                 }
               }
             }
           }
         }
+        __syncwarp();  // staging buffer is reused by the next chunk
       }
       tc_fence_before();
       __syncwarp();
