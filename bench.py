@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: a run with fewer layers is not a bench value")
     ap.add_argument("--cpu-sample-tokens", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the secondary WanVAE-decode measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -314,6 +315,33 @@ def main():
                 "avg_launch_ms": round(avg_ms, 4),
                 "share_of_step": round(sum(t for t, _ in self_attn) / max(ms_res, 1e-9), 4)}
 
+    # ---- WanVAE decode of this workload's latent (rank 0 only, as in the reference: text2video.py:260-261)
+    vae_rec = None
+    if rank == 0 and not args.no_vae:
+        try:
+            from wan.modules.vae import WanVAE
+            torch.manual_seed(3)
+            vae = WanVAE(vae_pth=None, device=dev)
+            zlat = torch.randn(*shape, device=dev)
+            vae.decode([zlat])                      # warm-up (packs weights, sizes the allocator)
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0v = mv.LAUNCHES
+            v0.record()
+            vid = vae.decode([zlat])[0]
+            v1.record()
+            torch.cuda.synchronize()
+            vms = v0.elapsed_time(v1)
+            vae_rec = {"metric": "vae_decode_fps", "value": round(vid.shape[1] / vms * 1e3, 2), "unit": "frames/s",
+                       "ms": round(vms, 1), "frames": int(vid.shape[1]), "out": list(vid.shape),
+                       "gpu_launches": mv.LAUNCHES - l0v, "finite": bool(torch.isfinite(vid).all().item())}
+            del vae, vid, zlat
+            torch.cuda.empty_cache()
+        except Exception as ex:  # the DiT number must still be reported
+            vae_rec = {"error": repr(ex)[:200]}
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         sps = K / (ms_res * 1e-3)
         sps_e2e = K / (ms_e2e * 1e-3)
@@ -331,6 +359,8 @@ def main():
                 "wall_ms_per_step": wall_res / K}
         if args.layers != LAYERS:
             line["INVALID"] = "debug run with %d of %d layers" % (args.layers, LAYERS)
+        if vae_rec is not None:
+            line["vae_decode"] = vae_rec
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_steps_per_sec(seq_len, args.cpu_sample_tokens)
         print(json.dumps(line), flush=True)

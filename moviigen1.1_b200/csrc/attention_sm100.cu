@@ -111,21 +111,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == 0 && lane == 0) {
+    // Both single-thread roles run WARP-UNIFORMLY (all 32 lanes execute the loops and poll the barriers) and only
+    // the TMA / tcgen05 instructions themselves are predicated on elect.sync: descriptors and addresses then live
+    // in uniform registers and ptxas emits back-to-back UTMALDG / UTCHMMA with no per-instruction
+    // "uniformisation" loop (with `if (lane == 0)` around the whole role each MMA cost ~100 issue cycles).
+    if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
-      mbar_expect_tx(q_full, 2 * kQTileBytes);
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kQTileBytes);
 #pragma unroll
-      for (int w = 0; w < 2; ++w)
+        for (int w = 0; w < 2; ++w)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       auto load_tile = [&](const CUtensorMap* tm, int j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_expect_tx(&kv_full[stage], kKVTileBytes);
-        tma_load_3d(sKV + stage * kKVTileBytes, tm, &kv_full[stage], 0, head, j * kBKV);
-        tma_load_3d(sKV + stage * kKVTileBytes + kKVHalfBytes, tm, &kv_full[stage], 64, head, j * kBKV);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[stage], kKVTileBytes);
+          tma_load_3d(sKV + stage * kKVTileBytes, tm, &kv_full[stage], 0, head, j * kBKV);
+          tma_load_3d(sKV + stage * kKVTileBytes + kKVHalfBytes, tm, &kv_full[stage], 64, head, j * kBKV);
+        }
+        __syncwarp();
         if (++stage == kKVStages) {
           stage = 0;
           phase ^= 1;
@@ -137,30 +147,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         load_tile(&tmV, j);
         if (j + 2 < n_kv) load_tile(&tmK, j + 2);
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ------------------------------ MMA issuer --------------------------------
       constexpr uint32_t idesc_qk = make_idesc_bf16(kBQ, kBKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
       const uint32_t sQ_addr = smem_u32(sQ);
       const uint32_t sKV_addr = smem_u32(sKV);
+      const uint64_t qdesc0 = make_desc_kmajor_sw128(sQ_addr);
+      const uint64_t kdesc0 = make_desc_kmajor_sw128(sKV_addr);
+      const uint64_t vdesc0 = make_desc_mnmajor_sw128(sKV_addr, kKVHalfBytes);
+      // S_w[b] = Q_w K^T : 8 x (M128 N64 K16).  Descriptor start addresses advance in 16-byte units.
       auto issue_qk = [&](int w, int st, int b) {
         const uint32_t d_tmem = tmem_base + (w * 2 + b) * 64;
+        const uint64_t qd = qdesc0 + ((w * kQTileBytes) >> 4);
+        const uint64_t kd = kdesc0 + ((st * kKVTileBytes) >> 4);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) {
-          const uint64_t adesc = make_desc_kmajor_sw128(sQ_addr + w * kQTileBytes + (k >> 2) * kQHalfBytes + (k & 3) * 32);
-          const uint64_t bdesc = make_desc_kmajor_sw128(sKV_addr + st * kKVTileBytes + (k >> 2) * kKVHalfBytes + (k & 3) * 32);
-          umma_ss(d_tmem, adesc, bdesc, idesc_qk, k != 0 ? 1u : 0u);
+          const uint32_t qo = ((k >> 2) * kQHalfBytes + (k & 3) * 32) >> 4;
+          const uint32_t ko = ((k >> 2) * kKVHalfBytes + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, qd + qo, kd + ko, idesc_qk, k != 0 ? 1u : 0u);
         }
       };
+      // O_w (+)= P_w[b] V : 4 x (M128 N128 K16), A = P from TMEM (32 columns of packed bf16 pairs)
       auto issue_pv = [&](int w, int st, int b, uint32_t acc) {
         const uint32_t d_tmem = tmem_base + 256 + w * 128;
-        const uint32_t a_tmem = tmem_base + (w * 2 + b) * 64;  // P: 32 columns of packed bf16 pairs
+        const uint32_t a_tmem = tmem_base + (w * 2 + b) * 64;
+        const uint64_t vd = vdesc0 + ((st * kKVTileBytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < kBKV / 16; ++k) {
-          // 16 keys = 2 eight-row groups of 1024 B; the two 64-wide d halves are kKVHalfBytes apart
-          const uint64_t bdesc = make_desc_mnmajor_sw128(sKV_addr + st * kKVTileBytes + k * 2048, kKVHalfBytes);
-          umma_ts(d_tmem, a_tmem + k * 8, bdesc, idesc_pv, (acc | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kBKV / 16; ++k) umma_ts(d_tmem, a_tmem + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -175,11 +189,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < 2 && j < n_kv; ++j) {
         mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
-        issue_qk(0, stage, j);
-        umma_commit(&s_full[0 * 2 + j]);
-        issue_qk(1, stage, j);
-        umma_commit(&s_full[1 * 2 + j]);
-        umma_commit(&kv_empty[stage]);
+        if (elect_one()) {
+          issue_qk(0, stage, j);
+          umma_commit(&s_full[0 * 2 + j]);
+          issue_qk(1, stage, j);
+          umma_commit(&s_full[1 * 2 + j]);
+          umma_commit(&kv_empty[stage]);
+        }
+        __syncwarp();
         advance();
       }
       for (int j = 0; j < n_kv; ++j) {
@@ -197,19 +214,30 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int w = 0; w < 2; ++w) {
           mbar_wait(&p_full[w * 2 + b], par);
           tc_fence_after();
-          issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
-          umma_commit(&o_done[w]);
-          if (more) {
-            if (w == 0) {
-              mbar_wait(&kv_full[kstage], kphase);
-              tc_fence_after();
+          if (elect_one()) {
+            issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
+            umma_commit(&o_done[w]);
+            if (w == 1) umma_commit(&kv_empty[vstage]);
+          }
+          __syncwarp();
+        }
+        if (more) {
+          // The score MMA (N = 64) overwrites the buffer P_w[b] lives in.  tcgen05.mma of DIFFERENT shapes are not
+          // ordered against each other by the pipe, so wait until P_w V_j has completed (o_done) before re-using
+          // the buffer; the pipe still holds the other tile's work meanwhile.
+          mbar_wait(&kv_full[kstage], kphase);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&o_done[w], j & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_qk(w, kstage, b);
+              umma_commit(&s_full[w * 2 + b]);
+              if (w == 1) umma_commit(&kv_empty[kstage]);
             }
-            issue_qk(w, kstage, b);
-            umma_commit(&s_full[w * 2 + b]);
+            __syncwarp();
           }
         }
-        umma_commit(&kv_empty[vstage]);
-        if (more) umma_commit(&kv_empty[kstage]);
       }
     }
   } else {

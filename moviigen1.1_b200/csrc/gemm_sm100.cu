@@ -87,14 +87,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(p, tile, m_blk, n_blk);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    // (warp-uniform loop, elect.sync only around the TMA issue: keeps addresses in uniform registers)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[stage], kStageBytes);
           if (p.a_kblock > 0) {
             const int k0 = kb * BK;
@@ -104,45 +105,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * BK, m_blk * BM);
           }
           tma_load_2d(sB + stage * kBBytes, &tmB, &full[stage], kb * BK, n_blk * BN);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    const uint64_t adesc0 = make_desc_kmajor_sw128(smem_u32(sA));
+    const uint64_t bdesc0 = make_desc_kmajor_sw128(smem_u32(sB));
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sA + stage * kABytes));
-          const uint64_t bdesc = make_desc_kmajor_sw128(smem_u32(sB + stage * kBBytes));
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + ((stage * kABytes) >> 4);
+          const uint64_t bdesc = bdesc0 + ((stage * kBBytes) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes (>>4 = 2) per K=16 step inside the 128B swizzle atom
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
         }
-        umma_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
@@ -194,6 +199,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (EPI == MV_EPI_RESID_F32 && p.gate != nullptr) g4[i] = __ldg(p.gate + col + i);
             }
         }
+        // residual epilogue: issue all eight row loads first so their latencies overlap (a load placed after the
+        // previous row's store could not be hoisted by the compiler: same pointer, possible aliasing)
+        float4 xres[8];
+        if constexpr (EPI == MV_EPI_RESID_F32) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int row = row_base + rr0 + 4 * k;
+            xres[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < p.M && col_full)
+              xres[k] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
+                                                         static_cast<int64_t>(row) * p.ldo + col);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int rr = rr0 + 4 * k;
@@ -222,7 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (col_full) {
                 float4 w;
                 if constexpr (EPI == MV_EPI_RESID_F32) {
-                  const float4 x = *reinterpret_cast<const float4*>(o);
+                  const float4 x = xres[k];
                   w.x = x.x + v[0] * g4[0]; w.y = x.y + v[1] * g4[1]; w.z = x.z + v[2] * g4[2]; w.w = x.w + v[3] * g4[3];
                 } else {
                   w.x = v[0]; w.y = v[1]; w.z = v[2]; w.w = v[3];

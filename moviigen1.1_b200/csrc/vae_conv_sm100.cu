@@ -22,12 +22,11 @@ namespace mv {
 constexpr int kConvBM = 128;
 constexpr int kConvTW = 16;   // tile width  (w)
 constexpr int kConvTH = 8;    // tile height (h)
-constexpr int kConvStages = 4;
+constexpr int kConvMaxStages = 16;
 constexpr int kConvThreads = 192;
 constexpr int kConvMaxTaps = 27;
-constexpr uint32_t kConvABytesMax = kConvBM * 64 * 2;   // 16 KB
-constexpr uint32_t kConvBBytesMax = 256 * 64 * 2;       // 32 KB
-constexpr uint32_t kConvSmem = kConvStages * (kConvABytesMax + kConvBBytesMax) + 1024 + 256;
+constexpr uint32_t kConvRingBytes = 200 * 1024;         // operand ring; the stage count adapts to the tile shape
+constexpr uint32_t kConvSmem = kConvRingBytes + 1024 + 512;
 
 struct ConvParams {
   const float* bias;            // [Cout] or null
@@ -45,6 +44,8 @@ struct ConvParams {
   int num_n, tiles_h, tiles_w, num_tiles, kblocks_per_tap;
   int out_mode;                 // 0: bf16 channels-last; 1: fp32 channel-first video [Cout_real,T,H,W] clamped to [-1,1]
   int cout_real;                // out_mode 1: number of real output channels (3)
+  int stages;                   // ring depth (<= kConvMaxStages)
+  uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes
 };
 
 template <int BK>
@@ -62,14 +63,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using Cfg = ConvCfg<BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kConvStages = p.stages;
+  const uint32_t kConvABytesMax = p.a_stage_bytes, kConvBBytesMax = p.b_stage_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + kConvStages * kConvABytesMax;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConvStages * (kConvABytesMax + kConvBBytesMax));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConvRingBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kConvStages;
-  uint64_t* tfull = bars + 2 * kConvStages;
-  uint64_t* tempty = bars + 2 * kConvStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConvStages + 4);
+  uint64_t* empty = bars + kConvMaxStages;
+  uint64_t* tfull = bars + 2 * kConvMaxStages;
+  uint64_t* tempty = bars + 2 * kConvMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConvMaxStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,55 +109,60 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int n_blk, t, h0, w0;
-        decode(tile, n_blk, t, h0, w0);
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
-            mbar_wait(&empty[stage], phase ^ 1);
+    // TMA producer: warp-uniform loop, elect.sync around the issue only
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int n_blk, t, h0, w0;
+      decode(tile, n_blk, t, h0, w0);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&full[stage], Cfg::kABytes + b_bytes);
             tma_load_4d(sA + stage * kConvABytesMax, &tmA, &full[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap],
                         t + p.dt[tap]);
             tma_load_2d(sB + stage * kConvBBytesMax, &tmB, &full[stage], tap * p.Cin + cb * BK, n_blk * p.BN);
-            if (++stage == kConvStages) {
-              stage = 0;
-              phase ^= 1;
-            }
           }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kConvBM, static_cast<uint32_t>(p.BN), 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 256;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * kConvABytesMax), 16, Cfg::kSBO, Cfg::kLayout);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * kConvBBytesMax), 16, Cfg::kSBO, Cfg::kLayout);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == kConvStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
       }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(kConvBM, static_cast<uint32_t>(p.BN), 0, 0);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, Cfg::kSBO, Cfg::kLayout);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, Cfg::kSBO, Cfg::kLayout);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256;
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + ((stage * kConvABytesMax) >> 4);
+          const uint64_t bdesc = bdesc0 + ((stage * kConvBBytesMax) >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == kb_total - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++stage == kConvStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
   } else {
     const int quad = warp & 3;
@@ -456,6 +464,10 @@ extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int 
   p.kblocks_per_tap = Cin / BK;
   p.out_mode = out_mode;
   p.cout_real = cout_real;
+  p.a_stage_bytes = (static_cast<uint32_t>(kConvBM * BK * 2) + 1023u) & ~1023u;
+  p.b_stage_bytes = (static_cast<uint32_t>(BN * BK * 2) + 1023u) & ~1023u;
+  p.stages = static_cast<int>(kConvRingBytes / (p.a_stage_bytes + p.b_stage_bytes));
+  if (p.stages > kConvMaxStages) p.stages = kConvMaxStages;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (BK == 64) return launch_conv<64>(tmA, tmB, p, st);
   if (BK == 32) return launch_conv<32>(tmA, tmB, p, st);
