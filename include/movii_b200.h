@@ -123,6 +123,34 @@ int mv_linear_f32_vec(const float* x, const float* W, const float* b, float* out
  * (sinusoidal_embedding_1d, model.py:15-25).  t: device int64/fp32 scalar. */
 int mv_sinusoid_embed(const void* t, int t_is_int64, float* out, int dim, mv_stream_t stream);
 
+/* ---- fused Ulysses exchange over NVLink peer memory (wan/distributed/xdit_context_parallel.py:155-198) --------- */
+/* The all-to-alls of the reference (xfuser -> NCCL) are fused into the producing kernels: each rank maps every peer's
+ * receive buffers (CUDA IPC) and the kernels store into them directly; a flag barrier orders producers and consumers.
+ * Receive buffer layout on every rank: [src rank][local token][heads_per_rank*128] (bf16). */
+
+/* Export / map a caller-owned device buffer.  handle64: 64 bytes; offset: of dptr inside its allocation. */
+int mv_ipc_export(const void* dptr, void* handle64, int64_t* offset, int64_t* alloc_bytes);
+int mv_ipc_open(const void* handle64, void** base_out);
+int mv_ipc_close(void* base);
+
+/* Cross-GPU barrier on the caller's stream: publishes `epoch` into slot `rank` of every peer's flag array
+ * (peer_flag_ptrs[i] = mapped base of rank i's uint32[8] flags; entry `rank` = own), then waits until all `world`
+ * local slots reached `epoch`.  Release/acquire at system scope: everything the previous kernels of this stream
+ * stored to peers is visible to the peers' next kernels.  Bounded wait (traps after 20 s instead of hanging). */
+int mv_sp_barrier(void* const* peer_flag_ptrs, void* local_flags, int rank, int world, unsigned int epoch,
+                  mv_stream_t stream);
+
+/* mv_qkv_prepare with the head scatter going straight to the destination ranks: head group d of local token m is
+ * written to dst_ptrs[d][src_rank][m][C/sp_world] (host array of sp_world mapped device pointers). */
+int mv_qkv_prepare_p2p(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* const* dst_ptrs,
+                       int src_rank, int sp_world, int M, int C, int head_dim, float eps, mv_stream_t stream);
+
+/* mv_attention_fwd whose epilogue returns each query row to its owner rank: row r -> o_dst[r / rows_per_rank]
+ * [src_rank][r % rows_per_rank][H*128] (ldo = row stride of the receive buffer, normally H*128). */
+int mv_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                             void* const* o_dst, int n_dst, int src_rank, int rows_per_rank, int64_t ldo, int Lq,
+                             int Lk, int H, float softmax_scale, mv_stream_t stream);
+
 /* ---- WanVAE decoder (wan/modules/vae.py) ------------------------------------------------------- */
 /* Activations are channels-last bf16 [T, H, W, C]; weights are packed per conv as bf16 [Cout_pad][tap][Cin]. */
 

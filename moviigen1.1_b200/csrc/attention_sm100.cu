@@ -42,6 +42,11 @@ struct AttnParams {
   int64_t ldo;
   int Lq, Lk, n_kv;
   float scale_log2;
+  // Ulysses return path fused into the epilogue: query row r belongs to rank r / rows_per_rank and is stored
+  // straight into that rank's receive buffer o_dst[rank][src_rank][r % rows_per_rank][H*128] (peer pointers over
+  // NVLink).  n_dst == 0: plain local output.
+  __nv_bfloat16* o_dst[8];
+  int n_dst, src_rank, rows_per_rank;
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -251,10 +256,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
+    // o_done[wg] completes one phase per P.V.  A parity wait is only meaningful if the waiter has observed every
+    // earlier phase (waiting for phase n while the barrier is still in phase n-2 passes spuriously), and with the
+    // score GEMM running two steps ahead this warpgroup CAN be two P.V's ahead of the tensor pipe — so the phases
+    // are consumed strictly in order: up to P.V(j-2) at the top of step j (normally complete long ago), up to
+    // P.V(j-1) before a rescale, up to P.V(n-1) before the epilogue.
+    int o_seen = 0;
+    auto wait_pv = [&](int upto) {  // returns when P.V(0..upto-1) of this tile have completed
+      while (o_seen < upto) {
+        mbar_wait(&o_done[wg], o_seen & 1);
+        ++o_seen;
+      }
+    };
 
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const uint32_t tS = tS0 + b * 64;
+      wait_pv(j - 1);
       mbar_wait(&s_full[wg * 2 + b], (j >> 1) & 1);
       tc_fence_after();
       uint32_t s[2][32];
@@ -284,7 +302,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const bool need = (m_new - m_run) * sl2 > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           // rescale O_w: the previous P.V of this tile must have landed first
-          mbar_wait(&o_done[wg], (j - 1) & 1);
+          wait_pv(j);
           tc_fence_after();
           const float alpha = fast_exp2((m_run - m_new) * sl2);
           l_run *= alpha;
@@ -329,11 +347,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
 
     // ------------------------------ final epilogue ----------------------------
-    mbar_wait(&o_done[wg], (n_kv - 1) & 1);
+    wait_pv(n_kv);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int row = q0 + wg * kBQ + quad * 32 + lane;
     __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * kD;
+    if (p.n_dst > 0 && row < p.Lq) {
+      const int dst = row / p.rows_per_rank;
+      const int rl = row - dst * p.rows_per_rank;
+      orow = p.o_dst[dst] + (static_cast<int64_t>(p.src_rank) * p.rows_per_rank + rl) * p.ldo + head * kD;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -364,9 +387,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 }  // namespace mv
 
-extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                void* o, int64_t ldo, int Lq, int Lk, int H, float softmax_scale,
-                                mv_stream_t stream) {
+static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                          int64_t ldo, int Lq, int Lk, int H, float softmax_scale, void* const* o_dst, int n_dst,
+                          int src_rank, int rows_per_rank, mv_stream_t stream) {
   using namespace mv;
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
@@ -375,7 +398,9 @@ extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64
              "mv_attention_fwd: row strides must be multiples of 8 elements");
   MV_REQUIRE(ldq >= (int64_t)H * kD && ldk >= (int64_t)H * kD && ldv >= (int64_t)H * kD && ldo >= (int64_t)H * kD,
              "mv_attention_fwd: row stride smaller than H*128");
-  MV_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0, "mv_attention_fwd: o must be 16-byte aligned");
+  MV_REQUIRE(n_dst > 0 || (o != nullptr && (reinterpret_cast<uintptr_t>(o) & 15) == 0),
+             "mv_attention_fwd: o must be 16-byte aligned");
+  MV_REQUIRE(n_dst >= 0 && n_dst <= 8, "mv_attention_fwd_scatter: at most 8 destinations");
   MV_REQUIRE(H <= 65535, "mv_attention_fwd: too many heads");
 
   CUtensorMap tmQ, tmK, tmV;
@@ -396,6 +421,19 @@ extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64
   p.Lk = Lk;
   p.n_kv = (Lk + kBKV - 1) / kBKV;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.n_dst = n_dst;
+  p.src_rank = src_rank;
+  p.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : 1;
+  for (int i = 0; i < 8; ++i) p.o_dst[i] = nullptr;
+  if (n_dst > 0) {
+    MV_REQUIRE(rows_per_rank > 0 && static_cast<int64_t>(rows_per_rank) * n_dst >= Lq && src_rank >= 0 && src_rank < n_dst,
+               "mv_attention_fwd_scatter: rows_per_rank*n_dst must cover Lq");
+    for (int i = 0; i < n_dst; ++i) {
+      MV_REQUIRE(o_dst[i] != nullptr && (reinterpret_cast<uintptr_t>(o_dst[i]) & 15) == 0,
+                 "mv_attention_fwd_scatter: destination %d null or misaligned", i);
+      p.o_dst[i] = reinterpret_cast<__nv_bfloat16*>(o_dst[i]);
+    }
+  }
 
   // fraction of exponentials evaluated on the FMA pipe: 0 = none, 1 = 1/4, 2 = 1/2 (MV_ATTN_EMU overrides)
   static int emu = -1;
@@ -416,4 +454,17 @@ extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64
   else attention_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   MV_CHECK_LAUNCH("attention_fwd_kernel");
   return MV_OK;
+}
+
+extern "C" int mv_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                void* o, int64_t ldo, int Lq, int Lk, int H, float softmax_scale,
+                                mv_stream_t stream) {
+  return attention_impl(q, ldq, k, ldk, v, ldv, o, ldo, Lq, Lk, H, softmax_scale, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int mv_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                        int64_t ldv, void* const* o_dst, int n_dst, int src_rank, int rows_per_rank,
+                                        int64_t ldo, int Lq, int Lk, int H, float softmax_scale, mv_stream_t stream) {
+  return attention_impl(q, ldq, k, ldk, v, ldv, nullptr, ldo, Lq, Lk, H, softmax_scale, o_dst, n_dst, src_rank,
+                        rows_per_rank, stream);
 }

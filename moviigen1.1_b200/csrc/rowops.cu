@@ -100,10 +100,18 @@ constexpr int kRmsVec = 4;  // uint4 per thread -> C <= 256*8*4 = 8192
 // out[dst][row][c'] with dst = col / (C / sp_world), c' = col % (C / sp_world) (rows = gridDim.x), i.e. the
 // head-scatter of xdit_context_parallel.py:185-190 is fused into this pass.  weight == nullptr skips the
 // norm (plain scatter copy, used for V).
+struct ScatterTable {
+  __nv_bfloat16* dst[8];  // per destination rank: base of its receive buffer [src rank][rows][C / sp_world]
+  int n;                  // 0: no table (use `out`), else sp_world
+  int src_rank;
+};
+
+// With a ScatterTable the head group of destination rank d is stored straight into rank d's HBM (a peer pointer
+// mapped over NVLink): the all-to-all of xdit_context_parallel.py:185-190 happens inside this pass.
 __global__ void __launch_bounds__(kRowThreads)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ weight,
                     const float* __restrict__ cs, int C, int head_dim, float eps,
-                    __nv_bfloat16* __restrict__ out, int sp_world) {
+                    __nv_bfloat16* __restrict__ out, int sp_world, const ScatterTable tab) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
@@ -155,11 +163,13 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __re
       }
       }
       (void)half;
-      if (out == nullptr) {
+      if (out == nullptr && tab.n == 0) {
         xr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
       } else {
         const int dst = col / cols_per_rank, cc = col - dst * cols_per_rank;
-        uint4* o = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(dst) * rows_total + row) * cols_per_rank + cc);
+        __nv_bfloat16* base = tab.n > 0 ? tab.dst[dst] : out;
+        const int slot = tab.n > 0 ? tab.src_rank : dst;
+        uint4* o = reinterpret_cast<uint4*>(base + (static_cast<int64_t>(slot) * rows_total + row) * cols_per_rank + cc);
         *o = make_uint4(u[0], u[1], u[2], u[3]);
       }
     }
@@ -385,24 +395,49 @@ extern "C" int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, co
   return mv_qkv_prepare(x_bf16, ld, weight, cs, nullptr, 1, M, C, head_dim, eps, stream);
 }
 
-extern "C" int mv_qkv_prepare(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16,
-                              int sp_world, int M, int C, int head_dim, float eps, mv_stream_t stream) {
+static int qkv_prepare_impl(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16,
+                            void* const* dst_ptrs, int src_rank, int sp_world, int M, int C, int head_dim, float eps,
+                            mv_stream_t stream) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(M > 0 && C > 0, "mv_rmsnorm_rope: empty problem");
-  MV_REQUIRE(sp_world >= 1 && C % sp_world == 0 && (C / sp_world) % head_dim == 0,
+  MV_REQUIRE(sp_world >= 1 && sp_world <= 8 && C % sp_world == 0 && (C / sp_world) % head_dim == 0,
              "mv_qkv_prepare: C=%d is not divisible into %d head groups", C, sp_world);
-  MV_REQUIRE(out_bf16 != nullptr || sp_world == 1, "mv_qkv_prepare: scatter needs an output buffer");
+  MV_REQUIRE(out_bf16 != nullptr || dst_ptrs != nullptr || sp_world == 1, "mv_qkv_prepare: scatter needs an output buffer");
   MV_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "mv_qkv_prepare: out must be 16B aligned");
   MV_REQUIRE(C % 8 == 0 && C <= kRowThreads * 8 * kRmsVec, "mv_rmsnorm_rope: C=%d must be a multiple of 8 and <= %d", C,
              kRowThreads * 8 * kRmsVec);
   MV_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "mv_rmsnorm_rope: rows must be 16B aligned");
   MV_REQUIRE(head_dim > 0 && head_dim % 2 == 0 && C % head_dim == 0, "mv_rmsnorm_rope: bad head_dim %d", head_dim);
+  ScatterTable tab;
+  tab.n = 0;
+  tab.src_rank = src_rank;
+  for (int i = 0; i < 8; ++i) tab.dst[i] = nullptr;
+  if (dst_ptrs != nullptr) {
+    MV_REQUIRE(src_rank >= 0 && src_rank < sp_world, "mv_qkv_prepare_p2p: bad source rank");
+    tab.n = sp_world;
+    for (int i = 0; i < sp_world; ++i) {
+      MV_REQUIRE(dst_ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(dst_ptrs[i]) & 15) == 0,
+                 "mv_qkv_prepare_p2p: destination %d is null or misaligned", i);
+      tab.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst_ptrs[i]);
+    }
+  }
   rmsnorm_rope_kernel<<<M, kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<__nv_bfloat16*>(x_bf16), ld, weight, cs, C, head_dim, eps,
-      reinterpret_cast<__nv_bfloat16*>(out_bf16), sp_world);
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), sp_world, tab);
   MV_CHECK_LAUNCH("rmsnorm_rope_kernel");
   return MV_OK;
+}
+
+extern "C" int mv_qkv_prepare(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16,
+                              int sp_world, int M, int C, int head_dim, float eps, mv_stream_t stream) {
+  return qkv_prepare_impl(x_bf16, ld, weight, cs, out_bf16, nullptr, 0, sp_world, M, C, head_dim, eps, stream);
+}
+
+extern "C" int mv_qkv_prepare_p2p(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* const* dst_ptrs,
+                                  int src_rank, int sp_world, int M, int C, int head_dim, float eps,
+                                  mv_stream_t stream) {
+  return qkv_prepare_impl(x_bf16, ld, weight, cs, nullptr, dst_ptrs, src_rank, sp_world, M, C, head_dim, eps, stream);
 }
 
 extern "C" int mv_patchify(const float* latent, void* a_bf16, int C, int F, int H, int W, int ph, int pw,

@@ -40,6 +40,13 @@ _SIGNATURES = {
     "mv_vae_rmsnorm_silu": [_ptr, _ptr, _ptr, _i64, _int, _int, _ptr],
     "mv_vae_latent_in": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _ptr],
     "mv_softmax_rows": [_ptr, _i64, _ptr, _i64, _int, _int, _f32, _ptr],
+    "mv_ipc_export": [_ptr, _ptr, _ptr, _ptr],
+    "mv_ipc_open": [_ptr, _ptr],
+    "mv_ipc_close": [_ptr],
+    "mv_sp_barrier": [_ptr, _ptr, _int, _int, _c.c_uint, _ptr],
+    "mv_qkv_prepare_p2p": [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _f32, _ptr],
+    "mv_attention_fwd_scatter": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _int, _int, _int, _i64, _int, _int, _int,
+                                 _f32, _ptr],
     "mv_patchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_head_unpatchify": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
                            _f32, _ptr],
@@ -310,3 +317,56 @@ def softmax_rows(s, p, n, scale):
     assert s.shape[1] >= n and p.shape[1] >= n
     _call("mv_softmax_rows", _p(s), s.stride(0), _p(p), p.stride(0), s.shape[0], n, float(scale), _stream())
     return p
+
+
+# ---- NVLink peer-to-peer plumbing (fused Ulysses exchange) -------------------------------------------------------
+def ptr_table(ptrs):
+    """Host array of device pointers (void* const*) for the *_p2p / *_scatter entry points."""
+    arr = (_c.c_void_p * 8)()
+    for i, v in enumerate(ptrs):
+        arr[i] = int(v)
+    return arr
+
+
+def ipc_export(t):
+    """(handle: bytes[64], offset: int, alloc_bytes: int) for the cudaMalloc allocation that holds tensor t."""
+    h = (_c.c_ubyte * 64)()
+    off, size = _c.c_int64(0), _c.c_int64(0)
+    _check(lib().mv_ipc_export(_c.c_void_p(t.data_ptr()), h, _c.byref(off), _c.byref(size)), "mv_ipc_export")
+    return bytes(h), off.value, size.value
+
+
+def ipc_open(handle):
+    base = _c.c_void_p(0)
+    buf = (_c.c_ubyte * 64).from_buffer_copy(handle)
+    _check(lib().mv_ipc_open(buf, _c.byref(base)), "mv_ipc_open")
+    return base.value
+
+
+def ipc_close(base):
+    _check(lib().mv_ipc_close(_c.c_void_p(base)), "mv_ipc_close")
+
+
+def sp_barrier(peer_flag_table, local_flags_ptr, rank, world, epoch):
+    _call("mv_sp_barrier", peer_flag_table, _c.c_void_p(local_flags_ptr), rank, world, _c.c_uint(epoch & 0xffffffff),
+          _stream())
+
+
+def qkv_prepare_p2p(x, weight, cs, dst_table, src_rank, sp_world, head_dim=128, eps=1e-6):
+    _req(x, torch.bfloat16, "x"); _req(weight, torch.float32, "weight"); _req(cs, torch.float32, "cs")
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, C = x.shape
+    _call("mv_qkv_prepare_p2p", _p(x), x.stride(0), _p(weight), _p(cs), dst_table, src_rank, sp_world, M, C, head_dim,
+          float(eps), _stream())
+
+
+def attention_scatter(q, k, v, o_table, n_dst, src_rank, rows_per_rank, ldo, softmax_scale=None):
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.bfloat16, n)
+        assert t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1 and t.stride(1) == 128, n
+    Lq, H, _ = q.shape
+    Lk = k.shape[0]
+    if softmax_scale is None:
+        softmax_scale = 128 ** -0.5
+    _call("mv_attention_fwd_scatter", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), o_table, n_dst,
+          src_rank, rows_per_rank, int(ldo), Lq, Lk, H, float(softmax_scale), _stream())

@@ -22,15 +22,24 @@ import torch.distributed as dist
 
 
 class UlyssesGroup:
-    """Process-group facts + communication buffers for one (rows, dim) shape."""
+    """Process-group facts + communication buffers for one (rows, dim) shape.
 
-    def __init__(self, group=None):
+    mode 'p2p' (default on CUDA, MOVII_SP_MODE=nccl to disable): the exchange is FUSED into the producing kernels —
+    every rank maps its peers' receive buffers over NVLink (CUDA IPC) and mv_qkv_prepare_p2p / mv_attention_fwd_scatter
+    store into them directly; two flag barriers per layer order producers and consumers (mv_sp_barrier).
+    mode 'nccl': 3 + 1 all_to_all_single calls per layer (the baseline; also what the gloo CPU tests exercise)."""
+
+    def __init__(self, group=None, mode=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        import os
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._buf = {}
+        self.mode = mode or os.environ.get("MOVII_SP_MODE", "p2p")
+        self._p2p = {}
+        self.epoch = 0
 
     def buffers(self, rows, dim, device, dtype=torch.bfloat16):
         key = (rows, dim, str(device))
@@ -42,6 +51,45 @@ class UlyssesGroup:
             b = dict(q_s=mk(), k_s=mk(), v_s=mk(), q_r=mk(), k_r=mk(), v_r=mk(), o_s=mk(), o_r=mk())
             self._buf[key] = b
         return b
+
+    # -- NVLink peer mapping (p2p mode) --------------------------------------------------------------------------
+    def p2p_buffers(self, mv, rows, dim, device):
+        """Receive slabs q_r, k_r, v_r, o_r [P, rows, dim/P] + flags on every rank, mapped into every peer."""
+        key = (rows, dim, str(device))
+        st = self._p2p.get(key)
+        if st is not None:
+            return st
+        for old in self._p2p.values():
+            for base in old["opened"]:
+                mv.ipc_close(base)
+        self._p2p.clear()
+        P, r = self.world, self.rank
+        n = rows * dim                                   # elements per slab
+        slab = torch.zeros(4 * n * 2 + 256, dtype=torch.uint8, device=device)
+        views = [slab[i * n * 2:(i + 1) * n * 2].view(torch.bfloat16).view(P, rows, dim // P) for i in range(4)]
+        flags_off = 4 * n * 2
+        handle, off, _ = mv.ipc_export(slab)
+        infos = [None] * P
+        dist.all_gather_object(infos, (handle, off), group=self.group)
+        bases, opened = [], []
+        for i, (h, o) in enumerate(infos):
+            if i == r:
+                bases.append(slab.data_ptr())
+            else:
+                b = mv.ipc_open(h)
+                opened.append(b)
+                bases.append(b + o)
+        st = dict(slab=slab, q_r=views[0], k_r=views[1], v_r=views[2], o_r=views[3], opened=opened,
+                  tab=[mv.ptr_table([b + i * n * 2 for b in bases]) for i in range(4)],
+                  flags=mv.ptr_table([b + flags_off for b in bases]), local_flags=slab.data_ptr() + flags_off)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)               # every rank has zeroed + mapped before anyone writes
+        self._p2p[key] = st
+        return st
+
+    def p2p_barrier(self, mv, st):
+        self.epoch += 1
+        mv.sp_barrier(st["flags"], st["local_flags"], self.rank, self.world, self.epoch)
 
     # -- collectives (plumbing) -----------------------------------------------------------------------
     def all_to_all(self, outs, ins):
@@ -80,6 +128,22 @@ def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, att
     P = grp.world
     C = bw.dim
     Hl = bw.num_heads // P
+    if grp.mode == "p2p" and prepare is None and attend is None:
+        # fused exchange: scatter stores go straight into the peers' receive buffers over NVLink
+        st = grp.p2p_buffers(mv, rows, C, ws.qkv.device)
+        qkv = ws.qkv[:rows]
+        mv.qkv_prepare_p2p(qkv[:, 0:C], bw.g_q, cs, st["tab"][0], grp.rank, P, 128, bw.eps)
+        mv.qkv_prepare_p2p(qkv[:, C:2 * C], bw.g_k, cs, st["tab"][1], grp.rank, P, 128, bw.eps)
+        mv.qkv_prepare_p2p(qkv[:, 2 * C:3 * C], None, None, st["tab"][2], grp.rank, P, 128, bw.eps)
+        grp.p2p_barrier(mv, st)                    # all q/k/v slabs complete everywhere
+        L = P * rows
+        hd = C // bw.num_heads
+        q = st["q_r"].view(L, Hl, hd)
+        k = st["k_r"].view(L, Hl, hd)[:kv_len_total]
+        v = st["v_r"].view(L, Hl, hd)[:kv_len_total]
+        mv.attention_scatter(q, k, v, st["tab"][3], P, grp.rank, rows, Hl * hd)
+        grp.p2p_barrier(mv, st)                    # all o slabs complete; also fences q/k/v reuse by the next layer
+        return st["o_r"]
     b = grp.buffers(rows, C, ws.qkv.device, ws.qkv.dtype)
     prepare = prepare or (lambda x, w, c, out: mv.qkv_prepare(x, w, c, out, P, 128, bw.eps))
     qkv = ws.qkv[:rows]

@@ -37,10 +37,20 @@ def main():
     seq_len = 384
     ok = True
     y1 = m([x], t, [ctx], seq_len)[0]
+    single_forward = m.forward
     m.forward = types.MethodType(usp_dit_forward, m)
-    ysp = m([x], t, [ctx], seq_len)[0]
-    rel = ((ysp - y1).double().norm() / y1.double().norm()).item()
-    ok = ok and rel <= 2e-3 and bool(torch.isfinite(ysp).all())
+    from xfuser.core.distributed import get_sp_group
+    rels = {}
+    for mode in ("nccl", "p2p"):
+        get_sp_group().ulysses.mode = mode
+        for rep in range(2):                       # twice: buffer reuse / barrier epochs across forwards
+            ysp = m([x], t, [ctx], seq_len)[0]
+        rel = ((ysp - y1).double().norm() / y1.double().norm()).item()
+        rels[mode] = rel
+        ok = ok and rel <= 2e-3 and bool(torch.isfinite(ysp).all())
+    rel = max(rels.values())
+    if rank == 0:
+        print("per-mode rel-L2:", rels, flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
