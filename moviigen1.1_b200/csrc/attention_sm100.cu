@@ -99,7 +99,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(q_full, 1);
     for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);  // released by both Q tiles' MMAs
+      mbar_init(&kv_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -182,78 +182,87 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int k = 0; k < kBKV / 16; ++k) umma_ts(d_tmem, a_tmem + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
       };
-      // Ring slot of the i-th tile in load order K_0 K_1 V_0 K_2 V_1 K_3 ... (K run out two steps before V).
-      auto idx_v = [&](int j) { return min(j + 2, n_kv) + j; };
-      auto idx_k = [&](int j) { return j < 2 ? j : 2 * j - 1; };
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kKVStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
       mbar_wait(q_full, 0);
-      // prologue: scores of steps 0 and 1 for both tiles
+      // prologue: scores of steps 0 and 1
       for (int j = 0; j < 2 && j < n_kv; ++j) {
-        mbar_wait(&kv_full[j], 0);
+        mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            issue_qk(w, j, j);
-            umma_commit(&s_full[w * 2 + j]);
-            umma_commit(&kv_empty[j]);     // kv_empty counts 2: one commit per Q tile
-          }
+          issue_qk(0, stage, j);
+          umma_commit(&s_full[0 * 2 + j]);
+          issue_qk(1, stage, j);
+          umma_commit(&s_full[1 * 2 + j]);
+          umma_commit(&kv_empty[stage]);
         }
         __syncwarp();
+        advance();
       }
-      // Main loop: each Q tile w is its own little state machine — P_w V_j as soon as P_w(j) and V_j are there, then
-      // Q_w K_{j+2}^T as soon as that P.V has drained (it overwrites the buffer P_w(j) lives in) and K_{j+2} is there.
-      // The two tiles are served in whatever order their softmax warpgroups deliver (non-blocking barrier probes),
-      // so a slow warpgroup never holds up the other tile's tensor work.
-      int jp0 = 0, jp1 = 0;                                  // next P.V step per tile
-      int jq0 = min(2, n_kv), jq1 = min(2, n_kv);            // next score step per tile
-      int os0 = 0, os1 = 0;                                  // P.V phases observed complete (consumed in order)
-      uint32_t idle = 0;
-      uint64_t t0 = 0;
-      auto serve = [&](const int w, int& jp, int& jq, int& o_seen) -> bool {
-        bool progressed = false;
-        if (jp < n_kv) {
-          const int j = jp, b = j & 1, iv = idx_v(j);
-          if (mbar_test(&p_full[w * 2 + b], (j >> 1) & 1) && mbar_test(&kv_full[iv % kKVStages], (iv / kKVStages) & 1)) {
+      for (int j = 0; j < n_kv; ++j) {
+        const int b = j & 1;
+        const uint32_t par = (j >> 1) & 1;
+        const int vstage = stage;
+        const uint32_t vphase = phase;
+        advance();
+        const bool more = (j + 2 < n_kv);
+        const int kstage = stage;
+        const uint32_t kphase = phase;
+        if (more) advance();
+        mbar_wait(&kv_full[vstage], vphase);
+        if (p.order == 1) {
+          // variant: Q_w K_{j+2}^T right behind P_w V_j (relies on the tensor pipe executing MMAs in issue order)
+          if (more) mbar_wait(&kv_full[kstage], kphase);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&p_full[w * 2 + b], par);
             tc_fence_after();
             if (elect_one()) {
-              issue_pv(w, iv % kKVStages, b, j > 0 ? 1u : 0u);
+              issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
               umma_commit(&o_done[w]);
-              umma_commit(&kv_empty[iv % kKVStages]);
+              if (w == 1) umma_commit(&kv_empty[vstage]);
+              if (more) {
+                issue_qk(w, kstage, b);
+                umma_commit(&s_full[w * 2 + b]);
+                if (w == 1) umma_commit(&kv_empty[kstage]);
+              }
             }
             __syncwarp();
-            ++jp;
-            progressed = true;
           }
+          continue;
         }
-        if (jq < n_kv && jq - 2 < jp) {
-          const int j = jq, b = j & 1, ik = idx_k(j);
-          while (o_seen < j - 1 && mbar_test(&o_done[w], o_seen & 1)) ++o_seen;
-          if ((p.order == 1 || o_seen >= j - 1) && mbar_test(&kv_full[ik % kKVStages], (ik / kKVStages) & 1)) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&p_full[w * 2 + b], par);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
+            umma_commit(&o_done[w]);
+            if (w == 1) umma_commit(&kv_empty[vstage]);
+          }
+          __syncwarp();
+        }
+        if (more) {
+          // The score MMA (N = 64) overwrites the buffer P_w[b] lives in.  tcgen05.mma of DIFFERENT shapes are not
+          // ordered against each other by the pipe, so wait until P_w V_j has completed (o_done) before re-using
+          // the buffer; the pipe still holds the other tile's work meanwhile.
+          mbar_wait(&kv_full[kstage], kphase);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&o_done[w], j & 1);
             tc_fence_after();
             if (elect_one()) {
-              issue_qk(w, ik % kKVStages, b);
+              issue_qk(w, kstage, b);
               umma_commit(&s_full[w * 2 + b]);
-              umma_commit(&kv_empty[ik % kKVStages]);
+              if (w == 1) umma_commit(&kv_empty[kstage]);
             }
             __syncwarp();
-            ++jq;
-            progressed = true;
-          }
-        }
-        return progressed;
-      };
-      while (jp0 < n_kv || jp1 < n_kv) {
-        const bool pr0 = serve(0, jp0, jq0, os0);
-        const bool pr1 = serve(1, jp1, jq1, os1);
-        const bool progressed = pr0 || pr1;
-        if (progressed) {
-          idle = 0;
-        } else if (((++idle) & 0xfff) == 0) {
-          if (t0 == 0) t0 = globaltimer_ns();
-          else if (globaltimer_ns() - t0 > MV_WAIT_TIMEOUT_NS) {
-            printf("mv: attention MMA scheduler stuck block(%d,%d) jp=%d,%d jq=%d,%d\n", blockIdx.x, blockIdx.y, jp0,
-                   jp1, jq0, jq1);
-            __trap();
           }
         }
       }
