@@ -47,7 +47,8 @@ struct AttnParams {
   // NVLink).  n_dst == 0: plain local output.
   __nv_bfloat16* o_dst[8];
   int n_dst, src_rank, rows_per_rank;
-  int order;  // 1: do not wait for P_w V_j to drain before Q_w K_{j+2}^T (relies on in-order tensor pipe; MV_ATTN_ORDER)
+  int order;  // 1 (default): Q_w K_{j+2}^T is issued right behind P_w V_j — the tensor pipe executes a CTA's MMAs in
+              // issue order; 0 (MV_ATTN_ORDER=0): additionally wait for P_w V_j to drain first
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -99,7 +100,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(q_full, 1);
     for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);  // released by both tiles' issuing warps
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -153,8 +154,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         load_tile(&tmV, j);
         if (j + 2 < n_kv) load_tile(&tmK, j + 2);
       }
-    } else if (warp == 1) {
-      // ------------------------------ MMA issuer --------------------------------
+    } else if (warp == 1 || warp == 2) {
+      // ------------------------------ MMA issuers -------------------------------
       constexpr uint32_t idesc_qk = make_idesc_bf16(kBQ, kBKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
       const uint32_t sQ_addr = smem_u32(sQ);
@@ -182,6 +183,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int k = 0; k < kBKV / 16; ++k) umma_ts(d_tmem, a_tmem + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
       };
+      // One issuing warp PER Q TILE (warp 1 -> tile 0, warp 2 -> tile 1): each blocks only on its own tile's
+      // barriers, so a late softmax warpgroup never delays the other tile's tensor work.  Both walk the K/V ring in
+      // the same order; a ring slot is released when both have committed (kv_empty counts 2).
+      const int w = warp - 1;
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() {
@@ -196,10 +201,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          issue_qk(0, stage, j);
-          umma_commit(&s_full[0 * 2 + j]);
-          issue_qk(1, stage, j);
-          umma_commit(&s_full[1 * 2 + j]);
+          issue_qk(w, stage, j);
+          umma_commit(&s_full[w * 2 + j]);
           umma_commit(&kv_empty[stage]);
         }
         __syncwarp();
@@ -216,54 +219,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t kphase = phase;
         if (more) advance();
         mbar_wait(&kv_full[vstage], vphase);
-        if (p.order == 1) {
-          // variant: Q_w K_{j+2}^T right behind P_w V_j (relies on the tensor pipe executing MMAs in issue order)
-          if (more) mbar_wait(&kv_full[kstage], kphase);
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            mbar_wait(&p_full[w * 2 + b], par);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
-              umma_commit(&o_done[w]);
-              if (w == 1) umma_commit(&kv_empty[vstage]);
-              if (more) {
-                issue_qk(w, kstage, b);
-                umma_commit(&s_full[w * 2 + b]);
-                if (w == 1) umma_commit(&kv_empty[kstage]);
-              }
-            }
-            __syncwarp();
+        if (more && p.order == 1) mbar_wait(&kv_full[kstage], kphase);
+        mbar_wait(&p_full[w * 2 + b], par);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
+          umma_commit(&o_done[w]);
+          umma_commit(&kv_empty[vstage]);
+          if (more && p.order == 1) {
+            // Q_w K_{j+2}^T right behind P_w V_j: the tensor pipe executes this thread's MMAs in issue order, so the
+            // score MMA overwrites the S/P buffer only after P_w V_j has read P from it
+            issue_qk(w, kstage, b);
+            umma_commit(&s_full[w * 2 + b]);
+            umma_commit(&kv_empty[kstage]);
           }
-          continue;
         }
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(&p_full[w * 2 + b], par);
+        __syncwarp();
+        if (more && p.order != 1) {
+          // conservative variant (MV_ATTN_ORDER=0): wait until P_w V_j has drained before re-using its buffer
+          mbar_wait(&kv_full[kstage], kphase);
+          mbar_wait(&o_done[w], j & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_pv(w, vstage, b, j > 0 ? 1u : 0u);
-            umma_commit(&o_done[w]);
-            if (w == 1) umma_commit(&kv_empty[vstage]);
+            issue_qk(w, kstage, b);
+            umma_commit(&s_full[w * 2 + b]);
+            umma_commit(&kv_empty[kstage]);
           }
           __syncwarp();
-        }
-        if (more) {
-          // The score MMA (N = 64) overwrites the buffer P_w[b] lives in.  tcgen05.mma of DIFFERENT shapes are not
-          // ordered against each other by the pipe, so wait until P_w V_j has completed (o_done) before re-using
-          // the buffer; the pipe still holds the other tile's work meanwhile.
-          mbar_wait(&kv_full[kstage], kphase);
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            mbar_wait(&o_done[w], j & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_qk(w, kstage, b);
-              umma_commit(&s_full[w * 2 + b]);
-              if (w == 1) umma_commit(&kv_empty[kstage]);
-            }
-            __syncwarp();
-          }
         }
       }
     }
@@ -278,11 +260,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
-    // o_done[wg] completes one phase per P.V.  A parity wait is only meaningful if the waiter has observed every
-    // earlier phase (waiting for phase n while the barrier is still in phase n-2 passes spuriously), and with the
-    // score GEMM running two steps ahead this warpgroup CAN be two P.V's ahead of the tensor pipe — so the phases
-    // are consumed strictly in order: up to P.V(j-2) at the top of step j (normally complete long ago), up to
-    // P.V(j-1) before a rescale, up to P.V(n-1) before the epilogue.
+    // o_done[wg] completes one phase per P.V.  A parity wait only means something while waiter and barrier are within
+    // one phase of each other: two phases ahead it passes spuriously, two phases behind it blocks for ever.  With
+    // the score GEMM running two steps ahead this warpgroup is no longer paced by the P.V's (v1 was), so the phases
+    // are consumed strictly in order and P.V(j-1) is always observed BEFORE P(j) is handed over (P.V(j) cannot
+    // complete before that, so the barrier can never run ahead) — that P.V had a whole step to finish, the wait is
+    // normally free.  A rescale needs the same wait, earlier.
     int o_seen = 0;
     auto wait_pv = [&](int upto) {  // returns when P.V(0..upto-1) of this tile have completed
       while (o_seen < upto) {
@@ -294,7 +277,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const uint32_t tS = tS0 + b * 64;
-      wait_pv(j - 1);
       mbar_wait(&s_full[wg * 2 + b], (j >> 1) & 1);
       tc_fence_after();
       uint32_t s[2][32];
@@ -361,6 +343,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
         }
       l_run += sum2.x + sum2.y;
+      wait_pv(j);
       tmem_st_x32(tS, pk);
       tc_wait_st();
       tc_fence_before();
@@ -447,7 +430,7 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     static int order = -1;
     if (order < 0) {
       const char* e = getenv("MV_ATTN_ORDER");
-      order = (e != nullptr && e[0] == '1') ? 1 : 0;
+      order = (e != nullptr && e[0] == '0') ? 0 : 1;   // default: Q K^T issued right behind P V (fastest)
     }
     p.order = order;
   }
