@@ -31,6 +31,7 @@ constexpr int kBKV = 64;            // keys per step
 constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
 constexpr int kDefaultEmu = 0;
+constexpr int kDefaultSkewNs = 0;
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
 constexpr uint32_t kQHalfBytes = kQTileBytes / 2;    // [128 x 64] 128B-swizzled sub-tile
 constexpr uint32_t kKVTileBytes = kBKV * kD * 2;     // 16 KB
@@ -47,8 +48,10 @@ struct AttnParams {
   // NVLink).  n_dst == 0: plain local output.
   __nv_bfloat16* o_dst[8];
   int n_dst, src_rank, rows_per_rank;
-  int order;  // 1 (default): Q_w K_{j+2}^T is issued right behind P_w V_j — the tensor pipe executes a CTA's MMAs in
-              // issue order; 0 (MV_ATTN_ORDER=0): additionally wait for P_w V_j to drain first
+  int skew_ns;  // initial delay of the second softmax warpgroup (MV_ATTN_SKEW): puts the two warpgroups' exp phases in
+                // antiphase so that they do not queue on the MUFU pipe at the same time
+  int order;  // 0 (default): Q_w K_{j+2}^T is issued after P_w V_j has drained (explicit o_done wait);
+              // 1 (MV_ATTN_ORDER=1): issued right behind it, relying on in-order execution of the tensor pipe
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -258,6 +261,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tS0 = tmem_base + lane_base + wg * 128;        // S_w[b] = tS0 + b * 64
     const uint32_t tO = tmem_base + lane_base + 256 + wg * 128;
     const float sl2 = p.scale_log2;
+    if (wg == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
     // o_done[wg] completes one phase per P.V.  A parity wait only means something while waiter and barrier are within
@@ -430,9 +434,15 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     static int order = -1;
     if (order < 0) {
       const char* e = getenv("MV_ATTN_ORDER");
-      order = (e != nullptr && e[0] == '0') ? 0 : 1;   // default: Q K^T issued right behind P V (fastest)
+      order = (e != nullptr && e[0] == '1') ? 1 : 0;   // default 0: same speed since each tile has its own issuer
     }
     p.order = order;
+    static int skew = -1;
+    if (skew < 0) {
+      const char* e = getenv("MV_ATTN_SKEW");
+      skew = e ? atoi(e) : kDefaultSkewNs;
+    }
+    p.skew_ns = skew;
   }
   p.n_dst = n_dst;
   p.src_rank = src_rank;

@@ -45,7 +45,9 @@ struct ConvParams {
   int out_mode;                 // 0: bf16 channels-last; 1: fp32 channel-first video [Cout_real,T,H,W] clamped to [-1,1]
   int cout_real;                // out_mode 1: number of real output channels (3)
   int stages;                   // ring depth (<= kConvMaxStages)
-  uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes
+  uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes (kps blocks each)
+  int kps;                      // k-blocks per ring slot (3 for Cin = 96: one whole tap per slot, 6 MMAs per barrier trip)
+  uint32_t a_block_bytes, b_block_bytes;
 };
 
 template <int BK>
@@ -115,20 +117,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int n_blk, t, h0, w0;
       decode(tile, n_blk, t, h0, w0);
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&full[stage], Cfg::kABytes + b_bytes);
-            tma_load_4d(sA + stage * kConvABytesMax, &tmA, &full[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap],
-                        t + p.dt[tap]);
-            tma_load_2d(sB + stage * kConvBBytesMax, &tmB, &full[stage], tap * p.Cin + cb * BK, n_blk * p.BN);
+      for (int kb = 0; kb < kb_total; kb += p.kps) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.kps) * (Cfg::kABytes + b_bytes));
+          for (int i = 0; i < p.kps; ++i) {
+            const int tap = (kb + i) / p.kblocks_per_tap;
+            const int cb = (kb + i) - tap * p.kblocks_per_tap;
+            tma_load_4d(sA + stage * kConvABytesMax + i * p.a_block_bytes, &tmA, &full[stage], cb * BK,
+                        w0 + p.dw[tap], h0 + p.dh[tap], t + p.dt[tap]);
+            tma_load_2d(sB + stage * kConvBBytesMax + i * p.b_block_bytes, &tmB, &full[stage],
+                        tap * p.Cin + cb * BK, n_blk * p.BN);
           }
-          __syncwarp();
-          if (++stage == kConvStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kConvStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -144,16 +149,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * 256;
-      for (int kb = 0; kb < kb_total; ++kb) {
+      for (int kb = 0; kb < kb_total; kb += p.kps) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t adesc = adesc0 + ((stage * kConvABytesMax) >> 4);
-          const uint64_t bdesc = bdesc0 + ((stage * kConvBBytesMax) >> 4);
+          for (int i = 0; i < p.kps; ++i) {
+            const uint64_t adesc = adesc0 + ((stage * kConvABytesMax + i * p.a_block_bytes) >> 4);
+            const uint64_t bdesc = bdesc0 + ((stage * kConvBBytesMax + i * p.b_block_bytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[stage]);
-          if (kb == kb_total - 1) umma_commit(&tfull[as]);
+          if (kb + p.kps >= kb_total) umma_commit(&tfull[as]);
         }
         __syncwarp();
         if (++stage == kConvStages) {
@@ -263,53 +271,81 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // y = silu( x / max(||x||_2, 1e-12) * sqrt(C) * gamma (+ beta) );  one warp per voxel, C <= 512, C % 8 == 0.
 // silu == 0 skips the activation (AttentionBlock.norm, vae.py:233,246).
 // --------------------------------------------------------------------------------------------
+// G lanes cooperate on one voxel (G = 16 for C <= 128, else 32), so a warp keeps 32/G voxels and every lane in
+// flight; two voxels per group are processed per iteration for memory-level parallelism.
+template <int G, int VPL>  // VPL = uint4 vectors per lane (C <= G * VPL * 8)
 __global__ void __launch_bounds__(256)
 rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
                        int64_t nvox, int C, int silu) {
+  constexpr int kUnroll = 2;
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int gl = lane & (G - 1);                  // lane inside the group
+  // the loop bound is WARP-uniform (full-mask shuffles inside): a warp covers (32/G)*kUnroll consecutive voxels
+  constexpr int kPerWarp = (32 / G) * kUnroll;
+  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int gw = lane / G;                        // group inside the warp
   const int nvec = C >> 3;
   const float scale = sqrtf(static_cast<float>(C));
-  for (int64_t vox = warp0; vox < nvox; vox += nwarps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + vox * C);
-    uint4 a[2];
-    float ss = 0.f;
+  float g[VPL][8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int idx = lane + 32 * j;
-      if (idx < nvec) {
-        a[j] = xr[idx];
-        const uint32_t u[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+  for (int j = 0; j < VPL; ++j) {
+    const int idx = gl + G * j;
+    if (idx < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx + 1);
+      g[j][0] = g0.x; g[j][1] = g0.y; g[j][2] = g0.z; g[j][3] = g0.w;
+      g[j][4] = g1.x; g[j][5] = g1.y; g[j][6] = g1.z; g[j][7] = g1.w;
+    }
+  }
+  for (int64_t vw = warp_id * kPerWarp; vw < nvox; vw += nwarps * kPerWarp) {
+    const int64_t v0 = vw + gw * kUnroll;
+    uint4 a[kUnroll][VPL];
+    float ss[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      ss[u] = 0.f;
+      const int64_t vox = v0 + u;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + vox * C);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        a[u][j] = make_uint4(0, 0, 0, 0);
+        if (vox < nvox && idx < nvec) a[u][j] = xr[idx];
+        const uint32_t w[4] = {a[u][j].x, a[u][j].y, a[u][j].z, a[u][j].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float lo = bf16_lo(u[k]), hi = bf16_hi(u[k]);
-          ss += lo * lo + hi * hi;
+          const float lo = bf16_lo(w[k]), hi = bf16_hi(w[k]);
+          ss[u] += lo * lo + hi * hi;
         }
       }
     }
-    ss = warp_sum(ss);
-    const float inv = scale / fmaxf(sqrtf(ss), 1e-12f);
-    uint4* yr = reinterpret_cast<uint4*>(y + vox * C);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int idx = lane + 32 * j;
-      if (idx < nvec) {
-        uint32_t u[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx + 1);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float lo = bf16_lo(u[k]) * inv * g[2 * k];
-          float hi = bf16_hi(u[k]) * inv * g[2 * k + 1];
-          if (silu) {
-            lo = lo / (1.f + __expf(-lo));
-            hi = hi / (1.f + __expf(-hi));
+      for (int o = G / 2; o > 0; o >>= 1) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t vox = v0 + u;
+      const float inv = scale / fmaxf(sqrtf(ss[u]), 1e-12f);
+      uint4* yr = reinterpret_cast<uint4*>(y + vox * C);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        if (vox < nvox && idx < nvec) {
+          uint32_t w[4] = {a[u][j].x, a[u][j].y, a[u][j].z, a[u][j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float lo = bf16_lo(w[k]) * inv * g[j][2 * k];
+            float hi = bf16_hi(w[k]) * inv * g[j][2 * k + 1];
+            if (silu) {
+              lo = lo / (1.f + __expf(-lo));
+              hi = hi / (1.f + __expf(-hi));
+            }
+            w[k] = pack_bf16(lo, hi);
           }
-          u[k] = pack_bf16(lo, hi);
+          yr[idx] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        yr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
       }
     }
   }
@@ -464,8 +500,11 @@ extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int 
   p.kblocks_per_tap = Cin / BK;
   p.out_mode = out_mode;
   p.cout_real = cout_real;
-  p.a_stage_bytes = (static_cast<uint32_t>(kConvBM * BK * 2) + 1023u) & ~1023u;
-  p.b_stage_bytes = (static_cast<uint32_t>(BN * BK * 2) + 1023u) & ~1023u;
+  p.kps = (BK == 32 && p.kblocks_per_tap % 3 == 0) ? 3 : 1;
+  p.a_block_bytes = (static_cast<uint32_t>(kConvBM * BK * 2) + 1023u) & ~1023u;
+  p.b_block_bytes = (static_cast<uint32_t>(BN * BK * 2) + 1023u) & ~1023u;
+  p.a_stage_bytes = p.a_block_bytes * p.kps;
+  p.b_stage_bytes = p.b_block_bytes * p.kps;
   p.stages = static_cast<int>(kConvRingBytes / (p.a_stage_bytes + p.b_stage_bytes));
   if (p.stages > kConvMaxStages) p.stages = kConvMaxStages;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -479,10 +518,18 @@ extern "C" int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* ga
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(nvox > 0 && C > 0 && C % 8 == 0 && C <= 512, "mv_vae_rmsnorm_silu: bad shape nvox=%lld C=%d", (long long)nvox, C);
-  int64_t blocks = (nvox + 7) / 8;
-  if (blocks > sm_count() * 32) blocks = sm_count() * 32;
-  rmsnorm_silu_cl_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x_cl), reinterpret_cast<__nv_bfloat16*>(y_cl), gamma, nvox, C, silu);
+  const int G = C <= 128 ? 16 : 32;
+  const int64_t per_warp = (32 / G) * 2;
+  const int64_t warps_needed = (nvox + per_warp - 1) / per_warp;
+  int64_t blocks = (warps_needed + 7) / 8;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_cl);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_cl);
+  if (C <= 128) rmsnorm_silu_cl_kernel<16, 1><<<static_cast<int>(blocks), 256, 0, st>>>(x, y, gamma, nvox, C, silu);
+  else if (C <= 256) rmsnorm_silu_cl_kernel<32, 1><<<static_cast<int>(blocks), 256, 0, st>>>(x, y, gamma, nvox, C, silu);
+  else rmsnorm_silu_cl_kernel<32, 2><<<static_cast<int>(blocks), 256, 0, st>>>(x, y, gamma, nvox, C, silu);
   MV_CHECK_LAUNCH("rmsnorm_silu_cl_kernel");
   return MV_OK;
 }

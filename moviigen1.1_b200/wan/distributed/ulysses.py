@@ -65,25 +65,46 @@ class UlyssesGroup:
         self._p2p.clear()
         P, r = self.world, self.rank
         n = rows * dim                                   # elements per slab
-        slab = torch.zeros(4 * n * 2 + 256, dtype=torch.uint8, device=device)
+        # Every rank takes the same decision at two agreement points (export, map); any failure anywhere switches the
+        # whole group to the NCCL exchange (still this library's kernels — there is no CPU or eager fallback).
+        slab, info, err = None, None, None
+        try:
+            slab = torch.zeros(4 * n * 2 + 256, dtype=torch.uint8, device=device)
+            handle, off, _ = mv.ipc_export(slab)
+            info = (handle, off)
+        except Exception as ex:
+            err = repr(ex)
+        infos = [None] * P
+        dist.all_gather_object(infos, info, group=self.group)
+        if any(i is None for i in infos):
+            self._p2p_error = err or "a peer could not export its buffer"
+            self.mode = "nccl"
+            return None
         views = [slab[i * n * 2:(i + 1) * n * 2].view(torch.bfloat16).view(P, rows, dim // P) for i in range(4)]
         flags_off = 4 * n * 2
-        handle, off, _ = mv.ipc_export(slab)
-        infos = [None] * P
-        dist.all_gather_object(infos, (handle, off), group=self.group)
         bases, opened = [], []
-        for i, (h, o) in enumerate(infos):
-            if i == r:
-                bases.append(slab.data_ptr())
-            else:
-                b = mv.ipc_open(h)
-                opened.append(b)
-                bases.append(b + o)
+        try:
+            for i, (h, o) in enumerate(infos):
+                if i == r:
+                    bases.append(slab.data_ptr())
+                else:
+                    b = mv.ipc_open(h)
+                    opened.append(b)
+                    bases.append(b + o)
+        except Exception as ex:
+            err = repr(ex)
+        torch.cuda.synchronize()
+        ok = torch.full((1,), 0.0 if err else 1.0, device=device)
+        dist.all_reduce(ok, group=self.group)        # also: every rank has zeroed + mapped before anyone writes
+        if int(round(ok.item())) != P:
+            for b in opened:
+                mv.ipc_close(b)
+            self._p2p_error = err or "a peer could not map the buffers"
+            self.mode = "nccl"
+            return None
         st = dict(slab=slab, q_r=views[0], k_r=views[1], v_r=views[2], o_r=views[3], opened=opened,
                   tab=[mv.ptr_table([b + i * n * 2 for b in bases]) for i in range(4)],
                   flags=mv.ptr_table([b + flags_off for b in bases]), local_flags=slab.data_ptr() + flags_off)
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)               # every rank has zeroed + mapped before anyone writes
         self._p2p[key] = st
         return st
 
@@ -131,6 +152,7 @@ def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, att
     if grp.mode == "p2p" and prepare is None and attend is None:
         # fused exchange: scatter stores go straight into the peers' receive buffers over NVLink
         st = grp.p2p_buffers(mv, rows, C, ws.qkv.device)
+    if grp.mode == "p2p" and prepare is None and attend is None:
         qkv = ws.qkv[:rows]
         mv.qkv_prepare_p2p(qkv[:, 0:C], bw.g_q, cs, st["tab"][0], grp.rank, P, 128, bw.eps)
         mv.qkv_prepare_p2p(qkv[:, C:2 * C], bw.g_k, cs, st["tab"][1], grp.rank, P, 128, bw.eps)
