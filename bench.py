@@ -282,23 +282,25 @@ def main():
     smi_index = cvd[local_rank] if local_rank < len(cvd) else local_rank
     sampler = ClockSampler(smi_index) if rank == 0 else None
     l0 = mv.LAUNCHES
-    rec = mv.time_kernels(["mv_attention_fwd"])
+    rec = mv.time_kernels(["mv_attention_fwd", "mv_attention_fwd_scatter"])
     ms_res, wall_res = timed(step_resident, K, Wm)
     launches = mv.LAUNCHES - l0
-    attn_events = list(rec.get("mv_attention_fwd", []))
+    # normalise both entry points to (Lq, Lk, H): plain = args[8:11]; scatter (fused Ulysses return) = args[11:14]
+    attn_events = [(s_, e_, (a[8], a[9], a[10])) for (s_, e_, a) in rec.get("mv_attention_fwd", [])] + \
+                  [(s_, e_, (a[11], a[12], a[13])) for (s_, e_, a) in rec.get("mv_attention_fwd_scatter", [])]
     mv.time_kernels(None)
     clocks = sampler.stop() if sampler else None
     ms_e2e, wall_e2e = timed(step_e2e, K, Wm + K)
     finite = bool(torch.isfinite(state["lat"]).all().item())
 
     # ---- dominant kernel: self-attention launches (Lk == sequence length), algorithmic FLOPs / event time
-    self_attn = [(s.elapsed_time(e), a) for (s, e, a) in attn_events if a[9] > TEXT_LEN]   # a[9] = Lk
+    self_attn = [(s.elapsed_time(e), a) for (s, e, a) in attn_events if a[1] > TEXT_LEN]   # a = (Lq, Lk, H)
     roof = None
     pk = peaks()
     if self_attn:
         avg_ms = sum(t for t, _ in self_attn) / len(self_attn)
         a = self_attn[0][1]
-        Lq, Lk, Hh = a[8], a[9], a[10]
+        Lq, Lk, Hh = a
         fl = 4.0 * Lq * Lk * Hh * 128
         ach = fl / (avg_ms * 1e-3) / 1e12
         traffic = None
