@@ -168,6 +168,15 @@ int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const 
                 int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t, int64_t os_h, int64_t os_w,
                 int nsplit, int64_t nsplit_off, mv_stream_t stream);
 
+/* mv_vae_conv (bf16 channels-last output) with the CONSUMER's RMS_norm + SiLU fused into the epilogue
+ * (vae.py:194-199: every conv of a ResidualBlock is fed silu(rms_norm(.))): norm_out[voxel,:] =
+ * silu(rms_norm(out[voxel,:]) * gamma) with the same addressing as out; out may be NULL when only the normalised
+ * tensor is consumed.  Requires Cout <= 256 (whole channel row in one tile). */
+int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed, const float* bias,
+                      const void* res_cl, void* out, int out_T, int out_H, int out_W, int Cout, int ntaps,
+                      const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t, int64_t os_h, int64_t os_w,
+                      const float* norm_gamma, void* norm_out, mv_stream_t stream);
+
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per voxel over channels (RMS_norm + nn.SiLU,
  * vae.py:39-54,194-199); channels-last bf16, in place allowed. */
 int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,

@@ -46,6 +46,8 @@ struct ConvParams {
   int cout_real;                // out_mode 1: number of real output channels (3)
   int stages;                   // ring depth (<= kConvMaxStages)
   uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes (kps blocks each)
+  const float* norm_gamma;      // fused RMS_norm + SiLU of the output row (needs BN == Cout): gamma [Cout] or null
+  __nv_bfloat16* norm_out;      // where silu(rms_norm(out)) goes (same addressing as out); `out` may then be null
   int kps;                      // k-blocks per ring slot (3 for Cin = 96: one whole tap per slot, 6 MMAs per barrier trip)
   uint32_t a_block_bytes, b_block_bytes;
 };
@@ -192,6 +194,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         nb = n0 - p.nsplit;
         off += p.nsplit_off;
       }
+      if (p.norm_out != nullptr) {
+        // Fused RMS_norm + SiLU of the output row (vae.py:39-54,194-199): the whole channel row of this voxel sits in
+        // this thread's TMEM lane, so the consumer's normalised input is produced here and the stand-alone
+        // normalisation pass over HBM disappears.  Pass 1: bias/residual, sum of squares, (optional) raw store;
+        // pass 2: re-read TMEM, normalise, SiLU, store.
+        float ss = 0.f;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const float inv = pass == 0 ? 0.f : sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 1
+          for (int c = 0; c < p.BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + c, v);
+            tc_wait_ld();
+            const int ncols = min(32, p.BN - c);
+            if (!ok) continue;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float b = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + c + i) : 0.f;
+              f[i] = i < ncols ? __uint_as_float(v[i]) + b : 0.f;
+            }
+            if (p.res != nullptr) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (8 * i < ncols) {
+                  const uint4 q = r4[i];
+                  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    f[8 * i + 2 * k] += bf16_lo(u[k]);
+                    f[8 * i + 2 * k + 1] += bf16_hi(u[k]);
+                  }
+                }
+              }
+            }
+            __nv_bfloat16* dst = nullptr;
+            if (pass == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                f[i] = bf16_round(f[i]);      // statistics of the value as it is stored
+                ss += f[i] * f[i];
+              }
+              if (p.out != nullptr) dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float gmm = i < ncols ? __ldg(p.norm_gamma + c + i) : 0.f;
+                const float y = bf16_round(f[i]) * inv * gmm;
+                f[i] = y / (1.f + __expf(-y));
+              }
+              dst = p.norm_out + off + c;
+            }
+            if (dst != nullptr) {
+              uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (8 * i < ncols) {
+                  uint4 q;
+                  q.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+                  q.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+                  q.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+                  q.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                  o4[i] = q;
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int c = 0; c < p.BN; c += 32) {   // BN multiple of 16: last chunk may be half valid
         uint32_t v[32];
         tmem_ld_x32(taddr + c, v);
@@ -431,11 +504,11 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 
 using namespace mv;
 
-extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
-                           const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
-                           int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
-                           int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
-                           mv_stream_t stream) {
+static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
+                         const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
+                         int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
+                         int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
+                         const float* norm_gamma, void* norm_out, mv_stream_t stream) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(ntaps >= 1 && ntaps <= kConvMaxTaps, "mv_vae_conv: ntaps=%d out of range", ntaps);
@@ -453,6 +526,10 @@ extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int 
     return MV_E_SHAPE;
   }
   MV_REQUIRE(nsplit == 0 || nsplit % BN == 0, "mv_vae_conv: nsplit must be a multiple of the N tile");
+  MV_REQUIRE((norm_out == nullptr) == (norm_gamma == nullptr), "mv_vae_conv_fused: norm_gamma and norm_out go together");
+  MV_REQUIRE(norm_out == nullptr || (BN == Cout && out_mode == 0 && nsplit == 0),
+             "mv_vae_conv_fused: the fused norm needs the whole channel row in one N tile (Cout=%d <= 256)", Cout);
+  MV_REQUIRE(out != nullptr || norm_out != nullptr, "mv_vae_conv: no output");
 
   CUtensorMap tmA, tmB;
   {
@@ -500,6 +577,8 @@ extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int 
   p.kblocks_per_tap = Cin / BK;
   p.out_mode = out_mode;
   p.cout_real = cout_real;
+  p.norm_gamma = norm_gamma;
+  p.norm_out = reinterpret_cast<__nv_bfloat16*>(norm_out);
   p.kps = (BK == 32 && p.kblocks_per_tap % 3 == 0) ? 3 : 1;
   p.a_block_bytes = (static_cast<uint32_t>(kConvBM * BK * 2) + 1023u) & ~1023u;
   p.b_block_bytes = (static_cast<uint32_t>(BN * BK * 2) + 1023u) & ~1023u;
@@ -511,6 +590,25 @@ extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int 
   if (BK == 64) return launch_conv<64>(tmA, tmB, p, st);
   if (BK == 32) return launch_conv<32>(tmA, tmB, p, st);
   return launch_conv<16>(tmA, tmB, p, st);
+}
+
+extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
+                           const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
+                           int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
+                           int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
+                           mv_stream_t stream) {
+  return vae_conv_impl(in_cl, in_T, in_H, in_W, Cin, w_packed, bias, res_cl, out, out_mode, out_T, out_H, out_W, Cout,
+                       cout_real, ntaps, taps_dt_dh_dw, o_base, os_t, os_h, os_w, nsplit, nsplit_off, nullptr, nullptr,
+                       stream);
+}
+
+extern "C" int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
+                                 const float* bias, const void* res_cl, void* out, int out_T, int out_H, int out_W,
+                                 int Cout, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t,
+                                 int64_t os_h, int64_t os_w, const float* norm_gamma, void* norm_out,
+                                 mv_stream_t stream) {
+  return vae_conv_impl(in_cl, in_T, in_H, in_W, Cin, w_packed, bias, res_cl, out, 0, out_T, out_H, out_W, Cout, Cout,
+                       ntaps, taps_dt_dh_dw, o_base, os_t, os_h, os_w, 0, 0, norm_gamma, norm_out, stream);
 }
 
 extern "C" int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "mv_unpatchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_vae_conv": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
                     _ptr, _i64, _i64, _i64, _i64, _int, _i64, _ptr],
+    "mv_vae_conv_fused": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _ptr, _i64,
+                          _i64, _i64, _i64, _ptr, _ptr, _ptr],
     "mv_vae_rmsnorm_silu": [_ptr, _ptr, _ptr, _i64, _int, _int, _ptr],
     "mv_vae_latent_in": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _ptr],
     "mv_softmax_rows": [_ptr, _i64, _ptr, _i64, _int, _int, _f32, _ptr],
@@ -370,3 +372,18 @@ def attention_scatter(q, k, v, o_table, n_dst, src_rank, rows_per_rank, ldo, sof
         softmax_scale = 128 ** -0.5
     _call("mv_attention_fwd_scatter", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), o_table, n_dst,
           src_rank, rows_per_rank, int(ldo), Lq, Lk, H, float(softmax_scale), _stream())
+
+
+def vae_conv_fused(x, conv, out, gamma, norm_out, res=None, o_base=0, os_t=0, os_h=0, os_w=0):
+    """vae_conv (bf16 channels-last) that also writes norm_out = silu(rms_norm(out) * gamma); out may be None."""
+    _req(x, torch.bfloat16, "x"); _req(conv.w, torch.bfloat16, "w"); _req(conv.b, torch.float32, "bias")
+    _req(res, torch.bfloat16, "res"); _req(out, torch.bfloat16, "out"); _req(norm_out, torch.bfloat16, "norm_out")
+    _req(gamma, torch.float32, "gamma")
+    assert x.dim() == 4 and x.is_contiguous() and norm_out.is_contiguous() and conv.w.is_contiguous()
+    assert out is None or (out.is_contiguous() and out.numel() == norm_out.numel())
+    T, H, W, Cin = x.shape
+    assert Cin == conv.cin and gamma.numel() == conv.cout and conv.cout == conv.cout_real
+    _call("mv_vae_conv_fused", _p(x), T, H, W, Cin, _p(conv.w), _p(conv.b), _p(res), _p(out), T, H, W, conv.cout,
+          conv.ntaps, conv.taps.data_ptr(), int(o_base), int(os_t), int(os_h), int(os_w), _p(gamma), _p(norm_out),
+          _stream())
+    return norm_out

@@ -218,13 +218,33 @@ class VaeEngine:
         return out
 
     # -- blocks -----------------------------------------------------------------------------------------------
-    def resblock(self, x, p):
+    # Every conv of a ResidualBlock consumes silu(rms_norm(.)).  Where the producing conv holds a whole channel row
+    # per thread (Cout <= 256: stages C and D, i.e. ~90 % of the bytes) that normalisation is fused into ITS epilogue
+    # (mv_vae_conv_fused) and the stand-alone pass over HBM disappears; `a_in` carries such a pre-normalised input.
+    @staticmethod
+    def _fusable(c):
+        return c.cout <= 256 and c.cout == c.cout_real
+
+    def resblock(self, x, p, a_in=None, next_gamma=None):
+        """Returns (x_new, a_next): a_next = silu(rms_norm(x_new) * next_gamma) if it could be fused, else None."""
         h = x if p["sc"] is None else self.conv(x, p["sc"])
-        a = self.normsilu(x, p["g0"], out=torch.empty_like(x))
-        y = self.conv(a, p["c2"])
+        a = a_in if a_in is not None else self.normsilu(x, p["g0"], out=torch.empty_like(x))
+        T, H, W, _ = x.shape
+        c2, c6 = p["c2"], p["c6"]
+        if self._fusable(c2):
+            y = torch.empty(T, H, W, c2.cout, dtype=BF16, device=self.device)
+            mv.vae_conv_fused(a, c2, None, p["g3"], y, o_base=0, os_t=H * W * c2.cout, os_h=W * c2.cout, os_w=c2.cout)
+        else:
+            y = self.conv(a, c2)
+            self.normsilu(y, p["g3"])
         del a
-        self.normsilu(y, p["g3"])
-        return self.conv(y, p["c6"], res=h)
+        if next_gamma is not None and self._fusable(c6):
+            out = torch.empty(T, H, W, c6.cout, dtype=BF16, device=self.device)
+            a_next = torch.empty_like(out)
+            mv.vae_conv_fused(y, c6, out, next_gamma, a_next, res=h, o_base=0, os_t=H * W * c6.cout, os_h=W * c6.cout,
+                              os_w=c6.cout)
+            return out, a_next
+        return self.conv(y, c6, res=h), None
 
     def attention(self, x, p):
         """vae.py:223-262: per-frame single-head attention, d = C, over the H*W positions."""
@@ -248,7 +268,7 @@ class VaeEngine:
             mv.gemm(P, vT, None, Of[f * hw:(f + 1) * hw], mv.MV_EPI_BF16)
         return self.conv(O, p["proj"], res=x)
 
-    def upsample(self, x, p):
+    def upsample(self, x, p, next_gamma=None):
         T, H, W, C = x.shape
         if p["mode"] == "upsample3d" and T > 1:
             T2 = 2 * T - 1
@@ -261,10 +281,17 @@ class VaeEngine:
             T = T2
         Co = C // 2
         out = torch.empty(T, 2 * H, 2 * W, Co, dtype=BF16, device=self.device)
+        a_next = None
+        fuse = next_gamma is not None and all(self._fusable(c) for c in p["par"].values())
+        if fuse:
+            a_next = torch.empty_like(out)
         for (a, b), c in p["par"].items():
-            mv.vae_conv(x, c, out, res=None, o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co,
-                        os_w=2 * Co)
-        return out
+            kw = dict(o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co, os_w=2 * Co)
+            if fuse:
+                mv.vae_conv_fused(x, c, out, next_gamma, a_next, **kw)
+            else:
+                mv.vae_conv(x, c, out, res=None, **kw)
+        return out, a_next
 
     # -- WanVAE.decode for one latent ---------------------------------------------------------------------------
     def decode(self, z):
@@ -274,14 +301,24 @@ class VaeEngine:
         x = torch.empty(T, h, w, Z, dtype=BF16, device=self.device)
         mv.vae_latent_in(z, self.w2, self.b2, self.mean, self.std, x)
         x = self.conv(x, self.conv1)
-        for kind, p in self.layers:
-            if kind == "res":
-                x = self.resblock(x, p)
-            elif kind == "attn":
-                x = self.attention(x, p)
+        a = None                                      # silu(rms_norm(x)) for the next consumer, when already fused
+        n = len(self.layers)
+        for i, (kind, p) in enumerate(self.layers):
+            # gamma of the norm the NEXT layer applies to this layer's output (None: attention / upsample read x raw)
+            if i + 1 < n:
+                nk, npar = self.layers[i + 1]
+                next_gamma = npar["g0"] if nk == "res" else None
             else:
-                x = self.upsample(x, p)
-        self.normsilu(x, self.head_gamma)
+                next_gamma = self.head_gamma
+            if kind == "res":
+                x, a = self.resblock(x, p, a_in=a, next_gamma=next_gamma)
+            elif kind == "attn":
+                x, a = self.attention(x, p), None
+            else:
+                x, a = self.upsample(x, p, next_gamma=next_gamma)
+        if a is None:
+            a = self.normsilu(x, self.head_gamma)
+        x = a
         T, H, W, _ = x.shape
         video = torch.empty(3, T, H, W, dtype=F32, device=self.device)
         mv.vae_conv(x, self.head, video, res=None, out_mode=1)
