@@ -29,8 +29,9 @@ constexpr int kD = 128;             // head dim
 constexpr int kBQ = 128;            // rows per Q tile
 constexpr int kBKV = 64;            // keys per step
 constexpr int kKVStages = 8;        // ring of 16 KB tiles
-constexpr int kAttnThreads = 352;   // warp 0 TMA, 1-2 MMA issuers, 3-6 / 7-10 softmax warpgroups
-constexpr int kDefaultEmu = 1;      // 1/4 of the exponentials on the FMA pipe (+5.7 % measured)
+constexpr int kAttnThreads = 384;
+constexpr int kDefaultEmu = 1;      // 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
+constexpr int kDefaultSkewNs = 0;   // skewing the two warpgroups' start had no measurable effect
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
 constexpr uint32_t kQHalfBytes = kQTileBytes / 2;    // [128 x 64] 128B-swizzled sub-tile
 constexpr uint32_t kKVTileBytes = kBKV * kD * 2;     // 16 KB
@@ -47,6 +48,8 @@ struct AttnParams {
   // NVLink).  n_dst == 0: plain local output.
   __nv_bfloat16* o_dst[8];
   int n_dst, src_rank, rows_per_rank;
+  int skew_ns;  // initial delay of the second softmax warpgroup (MV_ATTN_SKEW): puts the two warpgroups' exp phases in
+                // antiphase so that they do not queue on the MUFU pipe at the same time
   int order;  // 0 (default): Q_w K_{j+2}^T is issued after P_w V_j has drained (explicit o_done wait);
               // 1 (MV_ATTN_ORDER=1): issued right behind it, relying on in-order execution of the tensor pipe
 };
@@ -116,7 +119,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 3) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     // Both single-thread roles run WARP-UNIFORMLY (all 32 lanes execute the loops and poll the barriers) and only
     // the TMA / tcgen05 instructions themselves are predicated on elect.sync: descriptors and addresses then live
     // in uniform registers and ptxas emits back-to-back UTMALDG / UTCHMMA with no per-instruction
@@ -249,14 +253,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------ softmax warpgroups ------------------------
-    // (any four consecutive warps cover the four TMEM lane quadrants: quad = warp % 4)
-    const int wg = (warp - 3) >> 2;
+    const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS0 = tmem_base + lane_base + wg * 128;        // S_w[b] = tS0 + b * 64
     const uint32_t tO = tmem_base + lane_base + 256 + wg * 128;
     const float sl2 = p.scale_log2;
+    if (wg == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
     // o_done[wg] completes one phase per P.V.  A parity wait only means something while waiter and barrier are within
@@ -273,21 +278,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     };
 
-    // S(j+1) is fetched into registers (tcgen05.ld is asynchronous) BEFORE the arithmetic of step j starts — the
-    // score GEMM runs two steps ahead, so it is normally there already — which takes the barrier wake-up and the TMEM
-    // load latency of every step off the critical path.  Two register sets alternate (loop unrolled by two).
-    auto fetch_s = [&](int j, uint32_t (&dst)[2][32]) {
-      const int b = j & 1;
-      mbar_wait(&s_full[wg * 2 + b], (j >> 1) & 1);
-      tc_fence_after();
-      tmem_ld_x32(tS0 + b * 64, dst[0]);
-      tmem_ld_x32(tS0 + b * 64 + 32, dst[1]);
-    };
-    auto step = [&](int j, uint32_t (&s)[2][32], uint32_t (&s_next)[2][32]) {
+    for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const uint32_t tS = tS0 + b * 64;
-      tc_wait_ld();                                   // S(j) has landed in `s`
-      if (j + 1 < n_kv) fetch_s(j + 1, s_next);       // in flight during this step's arithmetic
+      mbar_wait(&s_full[wg * 2 + b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[2][32];
+      tmem_ld_x32(tS, s[0]);
+      tmem_ld_x32(tS + 32, s[1]);
+      tc_wait_ld();
       const int valid = p.Lk - j * kBKV;
       if (valid < kBKV) {
 #pragma unroll
@@ -331,40 +330,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float2 sc2 = make_float2(sl2, sl2);
       const float2 nm2 = make_float2(neg_m, neg_m);
       float2 sum2 = make_float2(0.f, 0.f);
-      // P is written back 16 keys (8 packed columns) at a time as it is produced: only 8 staging registers stay live
-      // next to the 64 + 64 score registers (this step's and the prefetched next step's)
+      uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i0 = 0; i0 < 32; i0 += 16) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = i0; i < i0 + 16; i += 4) {
-            const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-            const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-            float2 e01, e23;
-            e01.x = fast_exp2(x01.x);
-            e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
-            e23.x = fast_exp2(x23.x);
-            e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
-            sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
-            pk[(i - i0) >> 1] = pack_bf16(e01.x, e01.y);
-            pk[((i - i0) >> 1) + 1] = pack_bf16(e23.x, e23.y);
-          }
-          tmem_st_x8(tS + c * 16 + (i0 >> 1), pk);
+        for (int i = 0; i < 32; i += 4) {
+          const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+          const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+          float2 e01, e23;
+          e01.x = fast_exp2(x01.x);
+          e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
+          e23.x = fast_exp2(x23.x);
+          e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
+          sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
+          pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+          pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
         }
       l_run += sum2.x + sum2.y;
       wait_pv(j);
+      tmem_st_x32(tS, pk);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg * 2 + b]);
-    };
-    uint32_t sA[2][32], sB[2][32];
-    fetch_s(0, sA);
-    for (int j = 0; j < n_kv; j += 2) {
-      step(j, sA, sB);
-      if (j + 1 < n_kv) step(j + 1, sB, sA);
     }
 
     // ------------------------------ final epilogue ----------------------------
@@ -449,7 +437,12 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
       order = (e != nullptr && e[0] == '1') ? 1 : 0;   // default 0: same speed since each tile has its own issuer
     }
     p.order = order;
-
+    static int skew = -1;
+    if (skew < 0) {
+      const char* e = getenv("MV_ATTN_SKEW");
+      skew = e ? atoi(e) : kDefaultSkewNs;
+    }
+    p.skew_ns = skew;
   }
   p.n_dst = n_dst;
   p.src_rank = src_rank;

@@ -100,5 +100,7 @@ if __name__ == "__main__":
         bench_rowops()
     if "attn_one" in which:      # single launch for an ncu --set full capture
         bench_attn(75600, 5, None)
+    if "attn_720p" in which:     # the bench.py self-attention shape (one launch; for the ncu traffic capture)
+        bench_attn(75600, 40, None)
     if "gemm_one" in which:
         bench_gemm(75600, 5120, 5120, 2)
