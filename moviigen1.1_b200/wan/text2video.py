@@ -19,6 +19,7 @@ import torch.distributed as dist
 
 from .modules.model import WanModel
 from .modules.vae import WanVAE
+from .utils.fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
 from .utils.fm_solvers_unipc import FlowUniPCMultistepScheduler
 
 
@@ -122,12 +123,19 @@ class WanT2V:
         latent = torch.randn(*target_shape, dtype=torch.float32, device=self.device, generator=seed_g)
 
         with torch.no_grad():
-            if sample_solver != "unipc":
-                raise NotImplementedError("only the default 'unipc' solver is implemented (dpm++ is a §8f 'next' row)")
-            scheduler = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1,
-                                                    use_dynamic_shifting=False)
-            scheduler.set_timesteps(sampling_steps, device=self.device, shift=shift)
-            for t in scheduler.timesteps:
+            if sample_solver == "unipc":                      # text2video.py:206-213
+                scheduler = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1,
+                                                        use_dynamic_shifting=False)
+                scheduler.set_timesteps(sampling_steps, device=self.device, shift=shift)
+                timesteps = scheduler.timesteps
+            elif sample_solver == "dpm++":                    # text2video.py:214-223
+                scheduler = FlowDPMSolverMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1,
+                                                            use_dynamic_shifting=False)
+                timesteps, _ = retrieve_timesteps(scheduler, device=self.device,
+                                                  sigmas=get_sampling_sigmas(sampling_steps, shift))
+            else:
+                raise NotImplementedError("Unsupported solver.")
+            for t in timesteps:
                 latent = self.denoise_step(scheduler, latent, t, context, context_null, seq_len, guide_scale)
             videos = None
             if self.rank == 0 and decode:

@@ -142,6 +142,39 @@ def golden_vae(vae):
     return res
 
 
+def golden_dpmpp():
+    """Trajectory of the reference FlowDPMSolverMultistepScheduler driven like text2video.py:214-223 (needs the
+    diffusers stubs installed by golden_unipc)."""
+    import contextlib
+    import importlib.util
+    import io
+    du = sys.modules["diffusers.utils"]
+    tu = types.ModuleType("diffusers.utils.torch_utils")
+    tu.randn_tensor = lambda shape, generator=None, device=None, dtype=None: torch.randn(shape, generator=generator, dtype=dtype)
+    sys.modules["diffusers.utils.torch_utils"] = tu
+    du.torch_utils = tu
+    spec = importlib.util.spec_from_file_location(
+        "refwan_dpm", os.path.join(ref_loader.REF_ROOT, "wan", "utils", "fm_solvers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = {}
+    for steps in (3, 8, 20):
+        s = mod.FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        sig = mod.get_sampling_sigmas(steps, 5.0)
+        timesteps, _ = mod.retrieve_timesteps(s, device="cpu", sigmas=sig)
+        g = torch.Generator().manual_seed(50 + steps)
+        x = torch.randn(1, 16, 2, 4, 4, generator=g)
+        traj, outs = [x.clone()], []
+        with contextlib.redirect_stdout(io.StringIO()):
+            for t in timesteps:
+                v = torch.cos(2.0 * x) * 0.5 + 0.1 * torch.randn(x.shape, generator=g)
+                outs.append(v)
+                x = s.step(v, t, x, return_dict=False)[0]
+                traj.append(x.clone())
+        res[steps] = dict(timesteps=timesteps.clone(), sigmas=s.sigmas.clone(), model_outputs=outs, traj=traj)
+    return res
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     att, model, vae = ref_loader.load_reference()
@@ -149,6 +182,7 @@ def main():
     torch.save(golden_block_cfg1(model), os.path.join(OUT, "block_cfg1.pt"))
     torch.save(golden_model_tiny(model), os.path.join(OUT, "model_tiny_hd128.pt"))
     torch.save(golden_unipc(), os.path.join(OUT, "unipc.pt"))
+    torch.save(golden_dpmpp(), os.path.join(OUT, "dpmpp.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -106,3 +106,18 @@ def test_vae_state_dict_matches_reference_names():
     m = WanVAE_()
     ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert ours == g["param_shapes"]
+
+
+def test_dpmpp_scheduler_matches_reference():
+    """sample_solver='dpm++' (text2video.py:214-223): sigma schedule + 2M midpoint trajectory of the reference."""
+    from wan.utils.fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
+    gold = load("dpmpp.pt")
+    for steps, rec in gold.items():
+        s = FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        timesteps, n = retrieve_timesteps(s, device="cpu", sigmas=get_sampling_sigmas(steps, 5.0))
+        assert n == steps and torch.equal(timesteps, rec["timesteps"]) and torch.equal(s.sigmas, rec["sigmas"])
+        x = rec["traj"][0]
+        for i, t in enumerate(timesteps):
+            x = s.step(rec["model_outputs"][i], t, x, return_dict=False)[0]
+            ref = rec["traj"][i + 1]
+            assert (x - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), (steps, i)
