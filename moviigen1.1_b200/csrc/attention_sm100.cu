@@ -31,7 +31,8 @@ constexpr int kBKV = 64;            // keys per step
 constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
 constexpr int kDefaultEmu = 1;      // 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
-constexpr int kDefaultSkewNs = 0;   // skewing the two warpgroups' start had no measurable effect
+constexpr int kDefaultSkewNs = 0;
+constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
 constexpr uint32_t kQHalfBytes = kQTileBytes / 2;    // [128 x 64] 128B-swizzled sub-tile
 constexpr uint32_t kKVTileBytes = kBKV * kD * 2;     // 16 KB
@@ -48,6 +49,9 @@ struct AttnParams {
   // NVLink).  n_dst == 0: plain local output.
   __nv_bfloat16* o_dst[8];
   int n_dst, src_rank, rows_per_rank;
+  int pingpong;  // 1: the two softmax warpgroups take turns on the exp phase (named-barrier token), so that one
+                 // warpgroup's MUFU-bound exponentials overlap the other's barrier / TMEM / max bookkeeping instead of
+                 // both queueing on the 16-lane MUFU pipe at once (FA3/FA4 "ping-pong")
   int skew_ns;  // initial delay of the second softmax warpgroup (MV_ATTN_SKEW): puts the two warpgroups' exp phases in
                 // antiphase so that they do not queue on the MUFU pipe at the same time
   int order;  // 0 (default): Q_w K_{j+2}^T is issued after P_w V_j has drained (explicit o_done wait);
@@ -262,6 +266,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tO = tmem_base + lane_base + 256 + wg * 128;
     const float sl2 = p.scale_log2;
     if (wg == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);
+    // exp-phase token: named barrier 1 = "warpgroup 0 may run", 2 = "warpgroup 1 may run" (256 = 128 waiting + 128
+    // arriving threads).  Warpgroup 1 primes barrier 1 so that warpgroup 0 goes first.
+    if (p.pingpong && wg == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
     // o_done[wg] completes one phase per P.V.  A parity wait only means something while waiter and barrier are within
@@ -326,6 +333,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       }
+      if (p.pingpong) {
+        if (wg == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
       const float neg_m = -m_run * sl2;
       const float2 sc2 = make_float2(sl2, sl2);
       const float2 nm2 = make_float2(neg_m, neg_m);
@@ -347,6 +358,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
         }
       l_run += sum2.x + sum2.y;
+      if (p.pingpong) {   // hand the token over (warpgroup 1 keeps it after its last step: arrivals == waits)
+        if (wg == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        else if (j + 1 < n_kv) asm volatile("bar.arrive 1, 256;" ::: "memory");
+      }
       wait_pv(j);
       tmem_st_x32(tS, pk);
       tc_wait_st();
@@ -443,6 +458,12 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
       skew = e ? atoi(e) : kDefaultSkewNs;
     }
     p.skew_ns = skew;
+    static int pp = -1;
+    if (pp < 0) {
+      const char* e = getenv("MV_ATTN_PINGPONG");
+      pp = e ? atoi(e) : kDefaultPingPong;
+    }
+    p.pingpong = pp;
   }
   p.n_dst = n_dst;
   p.src_rank = src_rank;
