@@ -192,6 +192,30 @@ int mv_vae_latent_in(const float* z, const float* W2, const float* b2, const flo
 int mv_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int M, int N, float scale,
                     mv_stream_t stream);
 
+/* ---- umT5 text encoder (caller side of the hot path) --------------------------- */
+
+/* o[Lq,H,64] = softmax(q k^T + bias[h, (j - i) + bias_center] + key mask) v, no 1/sqrt(d) scaling, keys >= kv_len
+ * masked out; bf16 in/out, fp32 scores / softmax / accumulation.  q,k,v,o are [L, H, 64] views with row strides
+ * in elements; Lk <= 512 (the 128 x 512 score block of a CTA lives in TMEM).  bias is the per-head relative-position
+ * table (fp32 [H, bias_ld]) or NULL.  Replaces T5Attention.forward's einsum/softmax/einsum, wan/modules/t5.py:98-115,
+ * with the bias that T5RelativeEmbedding.forward (:233-243) materialises as [1,H,Lq,Lk]. */
+int mv_t5_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                    int64_t ldo, const float* bias, int64_t bias_ld, int bias_center, int Lq, int Lk, int kv_len,
+                    int H, mv_stream_t stream);
+
+/* out_bf16[r,:] = bf16( bf16(x[r,:] * rsqrt(mean(x[r,:]^2) + eps)) * weight ), x fp32: T5LayerNorm,
+ * wan/modules/t5.py:61-66 (the encoder keeps its residual stream in fp32 here). */
+int mv_t5_rmsnorm(const float* x, int64_t ldx, const float* weight, void* out, int64_t ldo, int rows, int C,
+                  float eps, mv_stream_t stream);
+
+/* out_f32[n,:] = float(table_bf16[clamp(ids[n]),:]): nn.Embedding lookup, wan/modules/t5.py:304. */
+int mv_embed_gather(const void* table, int64_t ldt, int64_t vocab, const int64_t* ids, float* out, int64_t ldo,
+                    int n, int C, mv_stream_t stream);
+
+/* out = bf16(a * b), bf16 [rows, C] each: the fc1(x) * gelu(gate(x)) product, wan/modules/t5.py:137. */
+int mv_mul_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int rows, int C,
+                mv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,10 @@ _SIGNATURES = {
                            _f32, _ptr],
     "mv_linear_f32_vec": [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _ptr],
     "mv_sinusoid_embed": [_ptr, _int, _ptr, _int, _ptr],
+    "mv_t5_attention": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _int, _ptr],
+    "mv_t5_rmsnorm": [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _f32, _ptr],
+    "mv_embed_gather": [_ptr, _i64, _i64, _ptr, _ptr, _i64, _int, _int, _ptr],
+    "mv_mul_bf16": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _ptr],
 }
 EXPORTED_SYMBOLS = ["mv_last_error", "mv_version", "mv_device_check"] + sorted(_SIGNATURES)
 
@@ -387,3 +391,49 @@ def vae_conv_fused(x, conv, out, gamma, norm_out, res=None, o_base=0, os_t=0, os
           conv.ntaps, conv.taps.data_ptr(), int(o_base), int(os_t), int(os_h), int(os_w), _p(gamma), _p(norm_out),
           _stream())
     return norm_out
+
+
+# ---- umT5 text encoder (wan/modules/t5.py) -------------------------------------------------------------------------
+def t5_attention(q, k, v, out, bias=None, bias_center=0, kv_len=None):
+    """q [Lq,H,64], k/v [Lk,H,64] bf16 views, out [Lq,H,64] bf16; bias fp32 [H, n] indexed by (j - i) + bias_center;
+    keys >= kv_len are masked out.  No softmax scale (T5)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+        assert t.dim() == 3 and t.shape[2] == 64 and t.stride(2) == 1 and t.stride(1) == 64, n
+    _req(bias, torch.float32, "bias")
+    Lq, H, _ = q.shape
+    Lk = k.shape[0]
+    assert v.shape[0] == Lk and k.shape[1] == H and v.shape[1] == H and out.shape[0] == Lq
+    if bias is not None:
+        assert bias.dim() == 2 and bias.shape[0] == H and bias.stride(1) == 1
+    _call("mv_t5_attention", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+          _p(bias), bias.stride(0) if bias is not None else 0, int(bias_center), Lq, Lk,
+          Lk if kv_len is None else int(kv_len), H, _stream())
+    return out
+
+
+def t5_rmsnorm(x, weight, out, eps=1e-6):
+    _req(x, torch.float32, "x"); _req(weight, torch.float32, "weight"); _req(out, torch.bfloat16, "out")
+    assert x.dim() == 2 and out.shape == x.shape and x.stride(1) == 1 and out.stride(1) == 1
+    assert weight.numel() == x.shape[1] and weight.is_contiguous()
+    _call("mv_t5_rmsnorm", _p(x), x.stride(0), _p(weight), _p(out), out.stride(0), x.shape[0], x.shape[1], float(eps),
+          _stream())
+    return out
+
+
+def embed_gather(table, ids, out):
+    _req(table, torch.bfloat16, "table"); _req(ids, torch.int64, "ids"); _req(out, torch.float32, "out")
+    assert table.dim() == 2 and table.stride(1) == 1 and ids.dim() == 1 and ids.is_contiguous()
+    assert out.shape == (ids.numel(), table.shape[1]) and out.stride(1) == 1
+    _call("mv_embed_gather", _p(table), table.stride(0), table.shape[0], _p(ids), _p(out), out.stride(0), ids.numel(),
+          table.shape[1], _stream())
+    return out
+
+
+def mul_bf16(a, b, out):
+    for t, n in ((a, "a"), (b, "b"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+        assert t.dim() == 2 and t.stride(1) == 1 and t.shape == a.shape, n
+    _call("mv_mul_bf16", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), a.shape[0], a.shape[1],
+          _stream())
+    return out

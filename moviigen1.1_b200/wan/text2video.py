@@ -2,8 +2,9 @@
 loop on the B200-native DiT engine and the native WanVAE decoder.
 
 Differences that are deliberate and documented:
-  * the umT5 text encoder is out of scope: when its checkpoint is absent, generate() takes pre-computed text
-    embeddings (`context=`, `context_null=`) or, for smoke/bench runs, deterministic synthetic embeddings;
+  * the umT5 text encoder (wan/modules/t5.py, sm_100a kernels) is used when its checkpoint and tokenizer exist
+    under checkpoint_dir (text2video.py:71-78); otherwise generate() takes pre-computed text embeddings
+    (`context=`, `context_null=`) or, for smoke/bench runs, deterministic synthetic embeddings;
   * random-init DiT / VAE weights are used when the checkpoints are absent (there are none on the box);
   * no FSDP (weights are replicated), no model offload to the CPU.
 """
@@ -44,11 +45,19 @@ class WanT2V:
         if t5_fsdp or dit_fsdp:
             from .distributed.fsdp import shard_model
             shard_model(None, device_id)  # raises: out of scope
-        self.text_encoder = None  # umT5 is out of scope (wan/modules/t5.py)
         self.vae_stride = config.vae_stride
         self.patch_size = config.patch_size
 
         ckpt = checkpoint_dir or ""
+        t5_pth = os.path.join(ckpt, config.t5_checkpoint)
+        t5_tok = os.path.join(ckpt, config.t5_tokenizer)
+        if os.path.isfile(t5_pth) and os.path.isdir(t5_tok):   # text2video.py:71-78
+            from .modules.t5 import T5EncoderModel
+            self.text_encoder = T5EncoderModel(text_len=config.text_len, dtype=config.t5_dtype, device=self.device,
+                                               checkpoint_path=t5_pth, tokenizer_path=t5_tok)
+        else:
+            logging.warning("no umT5 checkpoint/tokenizer under %r: prompts map to synthetic text embeddings", ckpt)
+            self.text_encoder = None
         vae_pth = os.path.join(ckpt, config.vae_checkpoint)
         self.vae = vae if vae is not None else WanVAE(vae_pth=vae_pth if os.path.isfile(vae_pth) else None,
                                                       device=self.device)
@@ -85,6 +94,8 @@ class WanT2V:
 
     # ------------------------------------------------------------------------------------------------
     def encode_prompt(self, prompt):
+        if self.text_encoder is not None:                      # text2video.py:174-184 (always on the GPU here)
+            return self.text_encoder([prompt], self.device)
         return [synthetic_text_embedding(prompt, 4096, self.config.text_len, self.device)]
 
     def denoise_step(self, scheduler, latent, t, context, context_null, seq_len, guide_scale):

@@ -30,3 +30,25 @@ def state_dict_like(shapes, seed):
     params = {k: torch.empty(v) for k, v in shapes.items()}
     fill_parameters(list(params.items()), seed)
     return params
+
+
+def fill_t5(module_or_named, seed):
+    """fill_parameters, then T5-specific conditioning: T5 attention has no 1/sqrt(d) scaling, so unit-variance q/k
+    rows would give near one-hot softmaxes; shrink q and make the relative-position bias O(1) so it matters."""
+    named = list(module_or_named.named_parameters() if hasattr(module_or_named, "named_parameters")
+                 else module_or_named)
+    fill_parameters(named, seed)
+    with torch.no_grad():
+        for name, p in named:
+            if name.endswith("attn.q.weight"):
+                p.mul_(0.25)
+            elif name.endswith("pos_embedding.embedding.weight"):
+                p.mul_(3.0)
+            elif name == "token_embedding.weight":
+                p.mul_(math.sqrt(p.shape[1]))
+
+
+def t5_state_dict_like(shapes, seed):
+    params = {k: torch.empty(v) for k, v in shapes.items()}
+    fill_t5(list(params.items()), seed)
+    return params

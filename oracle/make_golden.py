@@ -14,7 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref_loader  # noqa: E402
-from oracle.fill import fill_parameters  # noqa: E402
+from oracle.fill import fill_parameters, fill_t5  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -175,6 +175,30 @@ def golden_dpmpp():
     return res
 
 
+T5_TINY = dict(vocab=97, dim=128, dim_attn=128, dim_ffn=256, num_heads=2, num_layers=2, num_buckets=32,
+               shared_pos=False, dropout=0.1)
+
+
+def golden_t5():
+    """Reference T5Encoder (t5.py:267-312), tiny umT5-style config with head_dim 64 (what the sm_100a kernel
+    supports), fp32 / eval.  Cases: (L, valid) = (24, 17) one key box; (300, 263) two boxes, three query tiles and
+    relative distances past max_dist=128 (every bucket); (40, 40) no padding."""
+    t5 = ref_loader.load_reference_t5()
+    m = t5.T5Encoder(**T5_TINY).eval()
+    fill_t5(m, 505)
+    res = {"cfg": T5_TINY, "seed": 505, "cases": {},
+           "param_shapes": {k: tuple(v.shape) for k, v in m.state_dict().items()}}
+    for L, valid in ((24, 17), (300, 263), (40, 40)):
+        g = torch.Generator().manual_seed(600 + L)
+        ids = torch.randint(1, T5_TINY["vocab"], (L,), generator=g)
+        ids[valid:] = 0
+        mask = (torch.arange(L) < valid).long()
+        with torch.no_grad():
+            y = m(ids[None], mask[None])[0]
+        res["cases"][(L, valid)] = dict(ids=ids, mask=mask, y=y)
+    return res
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     att, model, vae = ref_loader.load_reference()
@@ -183,6 +207,7 @@ def main():
     torch.save(golden_model_tiny(model), os.path.join(OUT, "model_tiny_hd128.pt"))
     torch.save(golden_unipc(), os.path.join(OUT, "unipc.pt"))
     torch.save(golden_dpmpp(), os.path.join(OUT, "dpmpp.pt"))
+    torch.save(golden_t5(), os.path.join(OUT, "t5_encoder.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -85,3 +85,27 @@ def load_reference(patch_attention_for_cpu=True):
         model.flash_attention = sdpa_flash_attention
     _cache["mods"] = (att, model, vae)
     return _cache["mods"]
+
+
+def load_reference_t5():
+    """The reference's wan/modules/t5.py (T5Encoder etc.).  Its `from .tokenizers import HuggingfaceTokenizer` is
+    satisfied by a stub module (tokenizers.py needs `ftfy`, which is not installed, and is not arithmetic)."""
+    if "t5" in _cache:
+        return _cache["t5"]
+    load_reference()
+    tk = types.ModuleType("refwan.modules.tokenizers")
+
+    class HuggingfaceTokenizer:  # never constructed by the golden script
+        def __init__(self, *a, **k):
+            raise RuntimeError("tokenizer stub")
+
+    tk.HuggingfaceTokenizer = HuggingfaceTokenizer
+    sys.modules["refwan.modules.tokenizers"] = tk
+    # t5.py:478 evaluates torch.cuda.current_device() as a default argument at class-definition time
+    real = torch.cuda.current_device
+    torch.cuda.current_device = lambda: 0
+    try:
+        _cache["t5"] = _load("refwan.modules.t5", os.path.join(REF_ROOT, "wan", "modules", "t5.py"))
+    finally:
+        torch.cuda.current_device = real
+    return _cache["t5"]

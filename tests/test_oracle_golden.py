@@ -121,3 +121,58 @@ def test_dpmpp_scheduler_matches_reference():
             x = s.step(rec["model_outputs"][i], t, x, return_dict=False)[0]
             ref = rec["traj"][i + 1]
             assert (x - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), (steps, i)
+
+
+# ---- umT5 text encoder ---------------------------------------------------------------------------
+def _t5_cases():
+    g = load("t5_encoder.pt")
+    return g, sorted(g["cases"])
+
+
+@pytest.mark.parametrize("case", [(24, 17), (300, 263), (40, 40)])
+def test_t5_oracle_matches_reference(case):
+    """oracle/t5_oracle.py against the reference's own T5Encoder (fp32, CPU): tiny umT5-style config, padded and
+    unpadded prompts, relative distances past max_dist."""
+    from oracle import t5_oracle as T
+    from oracle.fill import t5_state_dict_like
+    g = load("t5_encoder.pt")
+    sd = t5_state_dict_like(g["param_shapes"], g["seed"])
+    c = g["cases"][case]
+    cfg = g["cfg"]
+    y = T.t5_encoder_forward(sd, c["ids"], c["mask"], cfg["num_heads"], cfg["num_buckets"], cfg["shared_pos"])
+    assert ((y - c["y"]).norm() / c["y"].norm()).item() < 1e-5
+    # the CUDA path's arithmetic contract (bf16 GEMM I/O) stays within 1.5e-2 of the fp32 reference
+    yb = T.t5_encoder_forward(sd, c["ids"], c["mask"], cfg["num_heads"], cfg["num_buckets"], cfg["shared_pos"],
+                              rb=T.bf16_rt)
+    assert ((yb - c["y"]).norm() / c["y"].norm()).item() < 1.5e-2
+    # valid rows do not depend on the padded tail: encoding only the prefix gives the same rows (what
+    # T5EncoderModel.__call__ relies on, t5.py:517)
+    n = case[1]
+    yp = T.t5_encoder_forward(sd, c["ids"][:n], None, cfg["num_heads"], cfg["num_buckets"], cfg["shared_pos"])
+    assert ((yp - c["y"][:n]).norm() / c["y"][:n].norm()).item() < 1e-5
+
+
+def test_t5_encoder_state_dict_and_bias_table_match_reference():
+    """Reference T5 checkpoints must load (same names / shapes), and the per-distance bias table the kernel indexes
+    equals the reference's materialised [N, Lq, Lk] bias."""
+    from oracle import t5_oracle as T
+    from wan.modules.t5 import T5Encoder, T5RelativeEmbedding
+    g = load("t5_encoder.pt")
+    m = T5Encoder(**g["cfg"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == g["param_shapes"]
+    rel = T5RelativeEmbedding(32, 4, bidirectional=True)
+    torch.nn.init.normal_(rel.embedding.weight)
+    for lq, lk in ((7, 7), (300, 300), (512, 512), (5, 9)):
+        tab = rel.table(lq, lk)                                  # [N, lq + lk - 1]
+        full = T.relative_bias(rel.embedding.weight.detach().float(), lq, lk, 32)
+        i = torch.arange(lq).view(-1, 1)
+        j = torch.arange(lk).view(1, -1)
+        assert torch.equal(tab[:, (j - i) + (lq - 1)], full)
+
+
+def test_tokenizer_cleaning_matches_reference_semantics():
+    from wan.modules import tokenizers as tk
+    assert tk.whitespace_clean("  a \n\t b  ") == "a b"
+    assert tk.basic_clean(" &amp;amp; x ") == "& x"
+    assert tk.canonicalize("Hello_World, it's  ME!") == "hello world its me"
+    assert tk.canonicalize("a.b|c.d", keep_punctuation_exact_string="|") == "ab|cd"
