@@ -1,0 +1,52 @@
+"""one full 14B DiT forward (40 layers, random-init) at L = 4k .. 128k tokens on one B200.
+Grids (F, H', W') = (1|2|4|8|16|32, 64, 64).  One JSON line per L: ms, model TFLOP/s (algorithmic FLOPs of §8d)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "moviigen1.1_b200"))
+import movii_b200 as mv  # noqa: E402
+from bench import fwd_flops  # noqa: E402
+from wan.configs import Config, t2v_14B  # noqa: E402
+from wan.modules.model import WanModel  # noqa: E402
+
+
+def main():
+    frames = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 8, 16, 32]
+    mv.device_check()
+    cfg = Config(t2v_14B)
+    torch.manual_seed(1234)
+    model = WanModel(model_type="t2v", patch_size=cfg.patch_size, text_len=cfg.text_len, in_dim=16, dim=cfg.dim,
+                     ffn_dim=cfg.ffn_dim, freq_dim=cfg.freq_dim, text_dim=4096, out_dim=16, num_heads=cfg.num_heads,
+                     num_layers=cfg.num_layers, window_size=cfg.window_size, qk_norm=True, cross_attn_norm=True,
+                     eps=cfg.eps, device="cuda", dtype=torch.bfloat16)
+    torch.nn.init.normal_(model.head.head.weight, std=0.02)
+    model.eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(0)
+    ctx = [torch.randn(512, 4096, generator=g).to(torch.bfloat16).cuda()]
+    t = torch.tensor([500], device="cuda")
+    for F in frames:
+        L = F * 64 * 64
+        lat = torch.randn(16, F, 128, 128, generator=g).cuda()
+        ts = []
+        for i in range(3):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = model([lat], t=t, context=ctx, seq_len=L)[0]
+            e.record()
+            torch.cuda.synchronize()
+            if i:
+                ts.append(s.elapsed_time(e))
+        ms = min(ts)
+        fl = fwd_flops(L)
+        print(json.dumps(dict(kind="dit_forward", L=L, grid=[F, 64, 64], ms=round(ms, 2),
+                              tflops=round(fl / ms / 1e9, 1), pflop=round(fl / 1e15, 4),
+                              finite=bool(torch.isfinite(out).all()))), flush=True)
+
+
+if __name__ == "__main__":
+    main()
