@@ -31,6 +31,7 @@ constexpr int kBKV = 64;            // keys per step
 constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
 constexpr int kDefaultEmu = 1;      // 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
+constexpr int kDefaultKStep = 64;    // MV_ATTN_KSTEP=128 selects the single-score-buffer / 128-key-step kernel below
 constexpr int kDefaultSkewNs = 0;
 constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
@@ -409,6 +410,301 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+
+// ================================================================================================================
+// 128-key-step variant (MV_ATTN_KSTEP=128): TMEM = S_0 | S_1 | O_0 | O_1 (4 x 128 fp32 columns), ONE score buffer per
+// Q tile, K/V tiles of 128 keys (4 x 32 KB ring).  The score MMA is M128 N128 K16: per instruction the A slice
+// (4 KB) + B slice (4 KB) are read from shared memory in the 64 cycles the MMA takes — at the 128 B/clk shared-memory
+// limit, whereas the N64 score MMA of the 64-key kernel needs 6 KB per 32 cycles (192 B/clk: smem-bound at 2/3 of the
+// tensor rate).  Per tile the chain softmax(j) -> P.V(j) -> Q.K(j+1)^T -> softmax(j+1) is serial (the score MMA is
+// issued right behind the P.V and overwrites the P/S buffer in tensor-pipe issue order); the two Q tiles fill each
+// other's gaps.  Half as many barrier hand-overs per key as the 64-key kernel.
+// ================================================================================================================
+constexpr int kBKV2 = 128;
+constexpr int kKVStages2 = 4;
+constexpr uint32_t kKVTileBytes2 = kBKV2 * kD * 2;     // 32 KB
+constexpr uint32_t kKVHalfBytes2 = kKVTileBytes2 / 2;  // [128 x 64] sub-tile
+constexpr uint32_t kAttnSmem2 = 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 1024 + 512;
+
+template <int EMU>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                        // 2 tiles
+  uint8_t* sKV = smem + 2 * kQTileBytes;     // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2);
+  uint64_t* q_full = bars;                    // 1
+  uint64_t* kv_full = bars + 1;               // kKVStages2
+  uint64_t* kv_empty = kv_full + kKVStages2;  // kKVStages2
+  uint64_t* s_full = kv_empty + kKVStages2;   // [w] -> 2
+  uint64_t* p_full = s_full + 2;              // [w] -> 2
+  uint64_t* o_done = p_full + 2;              // [w] -> 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int n_kv = (p.Lk + kBKV2 - 1) / kBKV2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKVStages2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);  // released by both tiles' issuing warps
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0) {
+      // ------------------------------ TMA producer: Q, K_0, then V_j, K_{j+1} ------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kQTileBytes);
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_tile = [&](const CUtensorMap* tm, int j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[stage], kKVTileBytes2);
+          tma_load_3d(sKV + stage * kKVTileBytes2, tm, &kv_full[stage], 0, head, j * kBKV2);
+          tma_load_3d(sKV + stage * kKVTileBytes2 + kKVHalfBytes2, tm, &kv_full[stage], 64, head, j * kBKV2);
+        }
+        __syncwarp();
+        if (++stage == kKVStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      load_tile(&tmK, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        load_tile(&tmV, j);
+        if (j + 1 < n_kv) load_tile(&tmK, j + 1);
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ------------------------------ MMA issuers: one warp per Q tile -------------------------------
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kBQ, kBKV2, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
+      const int w = warp - 1;
+      const uint64_t qdesc0 = make_desc_kmajor_sw128(smem_u32(sQ)) + ((w * kQTileBytes) >> 4);
+      const uint64_t kdesc0 = make_desc_kmajor_sw128(smem_u32(sKV));
+      const uint64_t vdesc0 = make_desc_mnmajor_sw128(smem_u32(sKV), kKVHalfBytes2);
+      const uint32_t tS = tmem_base + w * 128;
+      const uint32_t tO = tmem_base + 256 + w * 128;
+      // S_w = Q_w K^T : 8 x (M128 N128 K16)
+      auto issue_qk = [&](int st) {
+        const uint64_t kd = kdesc0 + ((st * kKVTileBytes2) >> 4);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint32_t qo = ((k >> 2) * kQHalfBytes + (k & 3) * 32) >> 4;
+          const uint32_t ko = ((k >> 2) * kKVHalfBytes2 + (k & 3) * 32) >> 4;
+          umma_ss(tS, qdesc0 + qo, kd + ko, idesc_qk, k != 0 ? 1u : 0u);
+        }
+      };
+      // O_w (+)= P_w V : 8 x (M128 N128 K16), A = P from TMEM (64 columns of packed bf16 pairs)
+      auto issue_pv = [&](int st, uint32_t acc) {
+        const uint64_t vd = vdesc0 + ((st * kKVTileBytes2) >> 4);
+#pragma unroll
+        for (int k = 0; k < kBKV2 / 16; ++k) umma_ts(tO, tS + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kKVStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_qk(stage);
+        umma_commit(&s_full[w]);
+        umma_commit(&kv_empty[stage]);
+      }
+      __syncwarp();
+      advance();
+      for (int j = 0; j < n_kv; ++j) {
+        const int vstage = stage;
+        const uint32_t vphase = phase;
+        advance();
+        const bool more = (j + 1 < n_kv);
+        const int kstage = stage;
+        const uint32_t kphase = phase;
+        if (more) advance();
+        mbar_wait(&kv_full[vstage], vphase);
+        if (more) mbar_wait(&kv_full[kstage], kphase);
+        mbar_wait(&p_full[w], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(vstage, j > 0 ? 1u : 0u);
+          umma_commit(&o_done[w]);
+          umma_commit(&kv_empty[vstage]);
+          if (more) {
+            // right behind P.V(j): this thread's MMAs execute in issue order, so the scores of step j+1 overwrite
+            // the S/P buffer only after P.V(j) has read P from it
+            issue_qk(kstage);
+            umma_commit(&s_full[w]);
+            umma_commit(&kv_empty[kstage]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ------------------------------ softmax warpgroups ------------------------
+    const int wg = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + wg * 128;
+    const uint32_t tO = tmem_base + lane_base + 256 + wg * 128;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
+    float l_run = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      // S(j) complete implies P.V(j-1) complete (same issuing thread, in order, and its commit came first), so the
+      // o_done wait below never blocks; it is taken every step so that every phase of the barrier is observed in order.
+      mbar_wait(&s_full[wg], j & 1);
+      if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, s[c]);
+      tc_wait_ld();
+      const int valid = p.Lk - j * kBKV2;
+      if (valid < kBKV2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
+        }
+      const float m_new = fmax3(m_run, mx0, mx1);
+      if (j == 0) {
+        m_run = m_new;
+      } else {
+        const bool need = (m_new - m_run) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = fast_exp2((m_run - m_new) * sl2);
+          l_run *= alpha;
+          m_run = m_new;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + c * 32, o);
+          }
+        }
+      }
+      const float neg_m = -m_run * sl2;
+      const float2 sc2 = make_float2(sl2, sl2);
+      const float2 nm2 = make_float2(neg_m, neg_m);
+      float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = h * 2 + cc;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+            const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+            float2 e01, e23;
+            e01.x = fast_exp2(x01.x);
+            e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
+            e23.x = fast_exp2(x23.x);
+            e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
+            pk[cc * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+            pk[cc * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
+          }
+        }
+        tmem_st_x32(tS + h * 32, pk);
+      }
+      l_run += sum2.x + sum2.y;
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[wg]);
+    }
+
+    // ------------------------------ final epilogue ----------------------------
+    mbar_wait(&o_done[wg], (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int row = q0 + wg * kBQ + quad * 32 + lane;
+    __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * kD;
+    if (p.n_dst > 0 && row < p.Lq) {
+      const int dst = row / p.rows_per_rank;
+      const int rl = row - dst * p.rows_per_rank;
+      orow = p.o_dst[dst] + (static_cast<int64_t>(p.src_rank) * p.rows_per_rank + rl) * p.ldo + head * kD;
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld_x32(tO + c * 32, o);
+      tc_wait_ld();
+      if (row < p.Lq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          dst[i] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace mv
 
 static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
@@ -434,9 +730,14 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
     return make_tmap_bf16(tm, base, 3, dims, str, box, true);
   };
+  static int kstep = -1;   // keys per softmax step: 64 (double-buffered scores) or 128 (MV_ATTN_KSTEP overrides)
+  if (kstep < 0) {
+    const char* e = getenv("MV_ATTN_KSTEP");
+    kstep = (e != nullptr && atoi(e) == 128) ? 128 : ((e != nullptr && atoi(e) == 64) ? 64 : kDefaultKStep);
+  }
   if ((rc = mk(&tmQ, q, ldq, Lq, kBQ)) != MV_OK) return rc;
-  if ((rc = mk(&tmK, k, ldk, Lk, kBKV)) != MV_OK) return rc;
-  if ((rc = mk(&tmV, v, ldv, Lk, kBKV)) != MV_OK) return rc;
+  if ((rc = mk(&tmK, k, ldk, Lk, kstep)) != MV_OK) return rc;
+  if ((rc = mk(&tmV, v, ldv, Lk, kstep)) != MV_OK) return rc;
 
   AttnParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
@@ -490,9 +791,22 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kstep == 128) {
+    if (emu == 2) attention_fwd_k128_kernel<2><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 1) attention_fwd_k128_kernel<1><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else attention_fwd_k128_kernel<0><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    MV_CHECK_LAUNCH("attention_fwd_k128_kernel");
+    return MV_OK;
+  }
   if (emu == 2) attention_fwd_kernel<2><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   else if (emu == 1) attention_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   else attention_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
