@@ -55,6 +55,7 @@ struct AttnParams {
                  // both queueing on the 16-lane MUFU pipe at once (FA3/FA4 "ping-pong")
   int skew_ns;  // initial delay of the second softmax warpgroup (MV_ATTN_SKEW): puts the two warpgroups' exp phases in
                 // antiphase so that they do not queue on the MUFU pipe at the same time
+  int splitp;  // 128-key kernel: 1 (default) = P.V's first 64-key half is issued as soon as that half of P is stored
   int order;  // 0 (default): Q_w K_{j+2}^T is issued after P_w V_j has drained (explicit o_done wait);
               // 1 (MV_ATTN_ORDER=1): issued right behind it, relying on in-order execution of the tensor pipe
 };
@@ -439,8 +440,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* kv_full = bars + 1;               // kKVStages2
   uint64_t* kv_empty = kv_full + kKVStages2;  // kKVStages2
   uint64_t* s_full = kv_empty + kKVStages2;   // [w] -> 2
-  uint64_t* p_full = s_full + 2;              // [w] -> 2
-  uint64_t* o_done = p_full + 2;              // [w] -> 2
+  uint64_t* p_full = s_full + 2;              // [w][half] -> 4: P is handed over in two 64-key halves
+  uint64_t* o_done = p_full + 4;              // [w] -> 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -460,7 +461,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[2 * i], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[2 * i + 1], 4);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
@@ -524,11 +526,12 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           umma_ss(tS, qdesc0 + qo, kd + ko, idesc_qk, k != 0 ? 1u : 0u);
         }
       };
-      // O_w (+)= P_w V : 8 x (M128 N128 K16), A = P from TMEM (64 columns of packed bf16 pairs)
-      auto issue_pv = [&](int st, uint32_t acc) {
+      // O_w (+)= P_w V : 8 x (M128 N128 K16), A = P from TMEM (64 columns of packed bf16 pairs); issued per 64-key
+      // half so that the first half can run while the softmax warpgroup is still exponentiating the second
+      auto issue_pv_half = [&](int st, int h, uint32_t acc) {
         const uint64_t vd = vdesc0 + ((st * kKVTileBytes2) >> 4);
 #pragma unroll
-        for (int k = 0; k < kBKV2 / 16; ++k) umma_ts(tO, tS + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
+        for (int k = 4 * h; k < 4 * h + 4; ++k) umma_ts(tO, tS + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -557,11 +560,16 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const uint32_t kphase = phase;
         if (more) advance();
         mbar_wait(&kv_full[vstage], vphase);
+        mbar_wait(&p_full[2 * w], j & 1);
+        if (!p.splitp) mbar_wait(&p_full[2 * w + 1], j & 1);
+        tc_fence_after();
+        if (elect_one()) issue_pv_half(vstage, 0, j > 0 ? 1u : 0u);
+        __syncwarp();
         if (more) mbar_wait(&kv_full[kstage], kphase);
-        mbar_wait(&p_full[w], j & 1);
+        mbar_wait(&p_full[2 * w + 1], j & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_pv(vstage, j > 0 ? 1u : 0u);
+          issue_pv_half(vstage, 1, 1u);
           umma_commit(&o_done[w]);
           umma_commit(&kv_empty[vstage]);
           if (more) {
@@ -658,12 +666,12 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           }
         }
         tmem_st_x32(tS + h * 32, pk);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * wg + h]);
       }
       l_run += sum2.x + sum2.y;
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[wg]);
     }
 
     // ------------------------------ final epilogue ----------------------------
@@ -765,6 +773,12 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
       pp = e ? atoi(e) : kDefaultPingPong;
     }
     p.pingpong = pp;
+    static int splitp = -1;
+    if (splitp < 0) {
+      const char* e = getenv("MV_ATTN_SPLITP");
+      splitp = e ? atoi(e) : 1;
+    }
+    p.splitp = splitp;
   }
   p.n_dst = n_dst;
   p.src_rank = src_rank;

@@ -1,31 +1,40 @@
 // tcgen05 GEMM for the DiT linears: out = epilogue(A[M,K] . W[N,K]^T + bias).
 //
 // Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer   (A tile 128x64, W tile 256x64 per stage, 128B-swizzled, 4-stage ring)
-//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1 M=128 N=256 K=16,
-//                               fp32 accumulators in TMEM, 2 accumulator stages = 512 columns)
+//   warp 0      TMA producer   (A tile 128x64, W tile BNx64 per stage, 128B-swizzled; BN = 256 with a 4-stage ring,
+//                               or BN = 64 with an 8-stage ring for skinny problems)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1 M=128 N=BN K=16,
+//                               fp32 accumulators in TMEM, 2 accumulator stages)
 //   warps 2..5  epilogue       (tcgen05.ld -> bias / GELU / gate+residual -> global), overlapped
 //                               with the next tile's main loop through the 2 TMEM stages
 // Tile order is grouped (16 M-tiles x all N-tiles) so that a wave's working set stays in L2.
 //
 // Replaces nn.Linear under bf16 autocast (cuBLASLt) — wan/modules/model.py:139-141,155,171-173,180,
 // 267-269,451-453 — and the patch-embedding Conv3d (:445-450,529).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
 namespace mv {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int kStages = 4;
 constexpr int kGroupM = 16;
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2;  // 16 KB
-constexpr uint32_t kBBytes = BN * BK * 2;  // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kEpiStageBytes = 4 * 4096;  // one 32x32 fp32 transpose buffer per epilogue warp
-constexpr uint32_t kGemmSmem = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// Two tile widths: N = 256 (4-stage ring) for the large-M DiT linears, and N = 64 (8-stage ring) for skinny
+// problems (M <= 512: umT5 encoder, text embedding) where a 256-wide tiling would leave most SMs without a tile —
+// those are weight-streaming bound, so what matters is how many SMs pull weights and how many bytes are in flight.
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 8;
+  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct GemmParams {
   const float* bias;
@@ -35,6 +44,9 @@ struct GemmParams {
   int M, N, K;
   int num_m, num_n, num_tiles, num_kb;
   int a_kblock;  // > 0: A is split along K into blocks of a_kblock columns (3-D tensor map {k, m, block})
+  int stream_out;  // 1: the output (and the fp32 residual it is read from) is much larger than L2 -> ld/st.global.cs
+                   // (evict-first), so that this one-touch traffic does not push the re-used A / W tiles out of L2
+                   // (ncu: 4.4 GB DRAM reads for 2.4 GB algorithmic on the 75600 x 5120 x 5120 residual GEMM)
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
@@ -46,10 +58,13 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   n_blk = within / gm;
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
+  constexpr int kStages = GemmCfg<BN>::kStages;
+  constexpr uint32_t kBBytes = GemmCfg<BN>::kBBytes;
+  constexpr uint32_t kStageBytes = GemmCfg<BN>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -207,9 +222,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < 8; ++k) {
             const int row = row_base + rr0 + 4 * k;
             xres[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < p.M && col_full)
-              xres[k] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
-                                                         static_cast<int64_t>(row) * p.ldo + col);
+            if (row < p.M && col_full) {
+              const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
+                                                                  static_cast<int64_t>(row) * p.ldo + col);
+              xres[k] = p.stream_out ? __ldcs(src) : *src;
+            }
           }
         }
 #pragma unroll
@@ -231,7 +248,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (EPI == MV_EPI_BF16 || EPI == MV_EPI_BF16_GELU) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo + col;
               if (col_full) {
-                *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                const uint2 w2 = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                if (p.stream_out) __stcs(reinterpret_cast<uint2*>(o), w2);
+                else *reinterpret_cast<uint2*>(o) = w2;
               } else {
                 for (int i = 0; i < 4 && col + i < p.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
               }
@@ -245,7 +264,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 } else {
                   w.x = v[0]; w.y = v[1]; w.z = v[2]; w.w = v[3];
                 }
-                *reinterpret_cast<float4*>(o) = w;
+                if (p.stream_out) __stcs(reinterpret_cast<float4*>(o), w);
+                else *reinterpret_cast<float4*>(o) = w;
               } else {
                 for (int i = 0; i < 4 && col + i < p.N; ++i) {
                   if constexpr (EPI == MV_EPI_RESID_F32) o[i] = o[i] + v[i] * g4[i];
@@ -273,18 +293,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kGemmSmem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GemmCfg<BN>::kSmem)));
     attr_set = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  gemm_bf16_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  gemm_bf16_kernel<EPI, BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(tmA, tmB, p);
   MV_CHECK_LAUNCH("gemm_bf16_kernel");
   return MV_OK;
+}
+
+template <int BN>
+static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int epilogue,
+                         cudaStream_t st) {
+  switch (epilogue) {
+    case MV_EPI_BF16: return launch_gemm<MV_EPI_BF16, BN>(tmA, tmB, p, st);
+    case MV_EPI_BF16_GELU: return launch_gemm<MV_EPI_BF16_GELU, BN>(tmA, tmB, p, st);
+    case MV_EPI_RESID_F32: return launch_gemm<MV_EPI_RESID_F32, BN>(tmA, tmB, p, st);
+    case MV_EPI_F32: return launch_gemm<MV_EPI_F32, BN>(tmA, tmB, p, st);
+    default: return launch_gemm<MV_EPI_F32_ROUND, BN>(tmA, tmB, p, st);
+  }
 }
 
 }  // namespace mv
@@ -321,10 +353,21 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
     rc = make_tmap_bf16(&tmA, A, 3, dims, str, box, true);
     if (rc != MV_OK) return rc;
   }
+  // tile width: 256 unless that leaves SMs idle on a skinny problem (MV_GEMM_BN=64|256 forces one, for tests)
+  const int num_m = (M + BM - 1) / BM;
+  int bn = (M <= 512 && num_m * ((N + 255) / 256) < 2 * sm_count()) ? 64 : 256;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("MV_GEMM_BN");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced == 64 || forced == 256) bn = forced;
+  }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t str[2] = {2, static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {BK, BN};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
     rc = make_tmap_bf16(&tmB, W, 2, dims, str, box, true);
     if (rc != MV_OK) return rc;
   }
@@ -336,19 +379,22 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
   p.M = M;
   p.N = N;
   p.K = K;
-  p.num_m = (M + BM - 1) / BM;
-  p.num_n = (N + BN - 1) / BN;
+  p.num_m = num_m;
+  p.num_n = (N + bn - 1) / bn;
   p.num_tiles = p.num_m * p.num_n;
   p.num_kb = (K + BK - 1) / BK;
   p.a_kblock = a_kblock;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (epilogue) {
-    case MV_EPI_BF16: return launch_gemm<MV_EPI_BF16>(tmA, tmB, p, st);
-    case MV_EPI_BF16_GELU: return launch_gemm<MV_EPI_BF16_GELU>(tmA, tmB, p, st);
-    case MV_EPI_RESID_F32: return launch_gemm<MV_EPI_RESID_F32>(tmA, tmB, p, st);
-    case MV_EPI_F32: return launch_gemm<MV_EPI_F32>(tmA, tmB, p, st);
-    default: return launch_gemm<MV_EPI_F32_ROUND>(tmA, tmB, p, st);
+  p.stream_out = (static_cast<int64_t>(M) * N * (f32_out ? 4 : 2) > (int64_t{96} << 20)) ? 1 : 0;
+  {
+    static int forced = -1;   // MV_GEMM_STREAM=0|1 overrides (A/B measurements)
+    if (forced < 0) {
+      const char* e = getenv("MV_GEMM_STREAM");
+      forced = e ? (atoi(e) ? 1 : 0) : 2;
+    }
+    if (forced != 2) p.stream_out = forced;
   }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return bn == 64 ? dispatch_gemm<64>(tmA, tmB, p, epilogue, st) : dispatch_gemm<256>(tmA, tmB, p, epilogue, st);
 }
 
 extern "C" int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,

@@ -18,7 +18,11 @@ def rel_l2(a, b):
 
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (300, 256, 192), (64, 128, 64),
-                                   (1000, 5120, 5120), (512, 1280, 4096), (4096, 768, 1536)])
+                                   (1000, 5120, 5120), (512, 1280, 4096), (4096, 768, 1536),
+                                   # skinny problems take the 64-wide tile (8-stage ring): umT5 shapes, ragged N / M
+                                   (32, 4096, 4096), (512, 10240, 4096), (100, 200, 64),
+                                   # M > 512 stays on the 256-wide tile, ragged in every dimension
+                                   (777, 1000, 320)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm(mv, M, N, K, epi):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K + epi)
