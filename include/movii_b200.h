@@ -192,6 +192,13 @@ int mv_vae_latent_in(const float* z, const float* W2, const float* b2, const flo
 int mv_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int M, int N, float scale,
                     mv_stream_t stream);
 
+/* Diagnostics only: mv_attention_fwd (128-key-step kernel) that also writes clock64 stamps of CTA (0, head 0) to
+ * trace[2 tiles][trace_steps][8] (uint64, device memory): 0 scores visible, 1 scores in registers, 2 row max done,
+ * 3 exponentials done, 4 P handed over, 5 P seen by the MMA warp, 6 P.V + next Q.K^T issued.  tools/attn_trace.py. */
+int mv_attention_fwd_trace(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                           int64_t ldo, int Lq, int Lk, int H, float softmax_scale, unsigned long long* trace,
+                           int trace_steps, mv_stream_t stream);
+
 /* ---- umT5 text encoder (caller side of the hot path) --------------------------- */
 
 /* o[Lq,H,64] = softmax(q k^T + bias[h, (j - i) + bias_center] + key mask) v, no 1/sqrt(d) scaling, keys >= kv_len

@@ -55,7 +55,8 @@ struct AttnParams {
                  // both queueing on the 16-lane MUFU pipe at once (FA3/FA4 "ping-pong")
   int skew_ns;  // initial delay of the second softmax warpgroup (MV_ATTN_SKEW): puts the two warpgroups' exp phases in
                 // antiphase so that they do not queue on the MUFU pipe at the same time
-  int splitp;  // 128-key kernel: 1 (default) = P.V's first 64-key half is issued as soon as that half of P is stored
+  unsigned long long* trace;  // diagnostics (mv_attention_fwd_trace): clock64 stamps of CTA (0, 0), see the entry point
+  int trace_steps;
   int order;  // 0 (default): Q_w K_{j+2}^T is issued after P_w V_j has drained (explicit o_done wait);
               // 1 (MV_ATTN_ORDER=1): issued right behind it, relying on in-order execution of the tensor pipe
 };
@@ -427,7 +428,7 @@ constexpr uint32_t kKVTileBytes2 = kBKV2 * kD * 2;     // 32 KB
 constexpr uint32_t kKVHalfBytes2 = kKVTileBytes2 / 2;  // [128 x 64] sub-tile
 constexpr uint32_t kAttnSmem2 = 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 1024 + 512;
 
-template <int EMU>
+template <int EMU, bool PP, bool TRACE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -440,8 +441,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* kv_full = bars + 1;               // kKVStages2
   uint64_t* kv_empty = kv_full + kKVStages2;  // kKVStages2
   uint64_t* s_full = kv_empty + kKVStages2;   // [w] -> 2
-  uint64_t* p_full = s_full + 2;              // [w][half] -> 4: P is handed over in two 64-key halves
-  uint64_t* o_done = p_full + 4;              // [w] -> 2
+  uint64_t* p_full = s_full + 2;              // [w] -> 2
+  uint64_t* o_done = p_full + 2;              // [w] -> 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -461,8 +462,7 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[2 * i], 4);  // one arrive per softmax warp
-      mbar_init(&p_full[2 * i + 1], 4);
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
@@ -526,12 +526,13 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           umma_ss(tS, qdesc0 + qo, kd + ko, idesc_qk, k != 0 ? 1u : 0u);
         }
       };
-      // O_w (+)= P_w V : 8 x (M128 N128 K16), A = P from TMEM (64 columns of packed bf16 pairs); issued per 64-key
-      // half so that the first half can run while the softmax warpgroup is still exponentiating the second
-      auto issue_pv_half = [&](int st, int h, uint32_t acc) {
+      // O_w (+)= P_w V : 8 x (M128 N128 K16), A = P from TMEM (64 columns of packed bf16 pairs).
+      // (Handing P over in two 64-key halves so that the first half of P.V overlaps the second half's exponentials
+      // was measured: the mid-step tcgen05.wait::st + barrier arrive cost 14 % (1358 -> 1172 TF/s) — not done.)
+      auto issue_pv = [&](int st, uint32_t acc) {
         const uint64_t vd = vdesc0 + ((st * kKVTileBytes2) >> 4);
 #pragma unroll
-        for (int k = 4 * h; k < 4 * h + 4; ++k) umma_ts(tO, tS + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kBKV2 / 16; ++k) umma_ts(tO, tS + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -560,16 +561,15 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const uint32_t kphase = phase;
         if (more) advance();
         mbar_wait(&kv_full[vstage], vphase);
-        mbar_wait(&p_full[2 * w], j & 1);
-        if (!p.splitp) mbar_wait(&p_full[2 * w + 1], j & 1);
-        tc_fence_after();
-        if (elect_one()) issue_pv_half(vstage, 0, j > 0 ? 1u : 0u);
-        __syncwarp();
         if (more) mbar_wait(&kv_full[kstage], kphase);
-        mbar_wait(&p_full[2 * w + 1], j & 1);
+        mbar_wait(&p_full[w], j & 1);
         tc_fence_after();
+        if constexpr (TRACE) {
+          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
+            p.trace[(w * p.trace_steps + j) * 8 + 5] = clock64();
+        }
         if (elect_one()) {
-          issue_pv_half(vstage, 1, 1u);
+          issue_pv(vstage, j > 0 ? 1u : 0u);
           umma_commit(&o_done[w]);
           umma_commit(&kv_empty[vstage]);
           if (more) {
@@ -581,6 +581,10 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           }
         }
         __syncwarp();
+        if constexpr (TRACE) {
+          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
+            p.trace[(w * p.trace_steps + j) * 8 + 6] = clock64();
+        }
       }
     }
   } else {
@@ -594,17 +598,24 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
+    // optional exp-phase token (MV_ATTN_PINGPONG=1): named barrier 1 = "warpgroup 0 may exponentiate", 2 = "warpgroup 1
+    // may"; warpgroup 1 primes barrier 1 so that warpgroup 0 goes first
+    if (PP && wg == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
     for (int j = 0; j < n_kv; ++j) {
       // S(j) complete implies P.V(j-1) complete (same issuing thread, in order, and its commit came first), so the
       // o_done wait below never blocks; it is taken every step so that every phase of the barrier is observed in order.
+      const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && lane == 0 && j < p.trace_steps;
+      unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
       mbar_wait(&s_full[wg], j & 1);
       if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);
       tc_fence_after();
+      if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
       uint32_t s[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, s[c]);
       tc_wait_ld();
+      if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
       const int valid = p.Lk - j * kBKV2;
       if (valid < kBKV2) {
 #pragma unroll
@@ -613,15 +624,14 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      float mx[4];   // one dependent chain per 32-column chunk (4 x 16 max3 deep instead of 2 x 32)
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 4; ++c) {
+        mx[c] = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
-        }
-      const float m_new = fmax3(m_run, mx0, mx1);
+        for (int i = 0; i < 32; i += 2) mx[c] = fmax3(mx[c], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+      }
+      const float m_new = fmax3(m_run, fmax3(mx[0], mx[1], mx[2]), mx[3]);
       if (j == 0) {
         m_run = m_new;
       } else {
@@ -641,6 +651,11 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           }
         }
       }
+      if constexpr (PP) {
+        if (wg == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
       const float neg_m = -m_run * sl2;
       const float2 sc2 = make_float2(sl2, sl2);
       const float2 nm2 = make_float2(neg_m, neg_m);
@@ -666,12 +681,18 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           }
         }
         tmem_st_x32(tS + h * 32, pk);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * wg + h]);
       }
       l_run += sum2.x + sum2.y;
+      if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
+      if constexpr (PP) {   // hand the token over (warpgroup 1 keeps it after its last step: arrivals == waits)
+        if (wg == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        else if (j + 1 < n_kv) asm volatile("bar.arrive 1, 256;" ::: "memory");
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[wg]);
+      if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
     }
 
     // ------------------------------ final epilogue ----------------------------
@@ -717,7 +738,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
 static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                           int64_t ldo, int Lq, int Lk, int H, float softmax_scale, void* const* o_dst, int n_dst,
-                          int src_rank, int rows_per_rank, mv_stream_t stream) {
+                          int src_rank, int rows_per_rank, mv_stream_t stream,
+                          unsigned long long* trace = nullptr, int trace_steps = 0) {
   using namespace mv;
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
@@ -773,13 +795,9 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
       pp = e ? atoi(e) : kDefaultPingPong;
     }
     p.pingpong = pp;
-    static int splitp = -1;
-    if (splitp < 0) {
-      const char* e = getenv("MV_ATTN_SPLITP");
-      splitp = e ? atoi(e) : 1;
-    }
-    p.splitp = splitp;
   }
+  p.trace = trace;
+  p.trace_steps = trace_steps;
   p.n_dst = n_dst;
   p.src_rank = src_rank;
   p.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : 1;
@@ -805,19 +823,28 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (kstep == 128) {
-    if (emu == 2) attention_fwd_k128_kernel<2><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else if (emu == 1) attention_fwd_k128_kernel<1><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else attention_fwd_k128_kernel<0><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+  if (kstep == 128 || p.trace != nullptr) {
+    if (p.trace != nullptr && p.pingpong) attention_fwd_k128_kernel<0, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (p.pingpong) attention_fwd_k128_kernel<0, true, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 2) attention_fwd_k128_kernel<2, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 1) attention_fwd_k128_kernel<1, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else attention_fwd_k128_kernel<0, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
     MV_CHECK_LAUNCH("attention_fwd_k128_kernel");
     return MV_OK;
   }
@@ -839,4 +866,18 @@ extern "C" int mv_attention_fwd_scatter(const void* q, int64_t ldq, const void* 
                                         int64_t ldo, int Lq, int Lk, int H, float softmax_scale, mv_stream_t stream) {
   return attention_impl(q, ldq, k, ldk, v, ldv, nullptr, ldo, Lq, Lk, H, softmax_scale, o_dst, n_dst, src_rank,
                         rows_per_rank, stream);
+}
+
+// Diagnostics: mv_attention_fwd on the 128-key-step kernel with clock64 stamps of CTA (0, head 0) written to
+// trace[tile w (2)][step (trace_steps)][8]: 0 = scores visible to the softmax warpgroup, 1 = scores in registers,
+// 2 = row max done, 3 = exponentials done, 4 = P handed over, 5 = P seen by the MMA warp, 6 = P.V + next Q.K^T issued.
+extern "C" int mv_attention_fwd_trace(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                      void* o, int64_t ldo, int Lq, int Lk, int H, float softmax_scale,
+                                      unsigned long long* trace, int trace_steps, mv_stream_t stream) {
+  if (trace == nullptr || trace_steps <= 0) {
+    mv::set_error("mv_attention_fwd_trace: trace buffer required");
+    return MV_E_SHAPE;
+  }
+  return attention_impl(q, ldq, k, ldk, v, ldv, o, ldo, Lq, Lk, H, softmax_scale, nullptr, 0, 0, 0, stream, trace,
+                        trace_steps);
 }

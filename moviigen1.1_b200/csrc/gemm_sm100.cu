@@ -25,9 +25,10 @@ constexpr int kGemmThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kEpiStageBytes = 4 * 4096;  // one 32x32 fp32 transpose buffer per epilogue warp
 
-// Two tile widths: N = 256 (4-stage ring) for the large-M DiT linears, and N = 64 (8-stage ring) for skinny
-// problems (M <= 512: umT5 encoder, text embedding) where a 256-wide tiling would leave most SMs without a tile —
-// those are weight-streaming bound, so what matters is how many SMs pull weights and how many bytes are in flight.
+// Two tile widths: N = 256 (4-stage ring) for the DiT linears, and N = 64 (8-stage ring) for single-M-tile problems
+// (M <= 128: umT5 encoder on a typical prompt) where a 256-wide tiling would leave most SMs without a tile — those
+// are weight-streaming bound, so what matters is how many SMs pull weights and how many bytes are in flight
+// (umT5 encode of 128 tokens: 7.9 -> 5.8 ms).
 template <int BN>
 struct GemmCfg {
   static constexpr int kStages = BN == 256 ? 4 : 8;
@@ -44,9 +45,9 @@ struct GemmParams {
   int M, N, K;
   int num_m, num_n, num_tiles, num_kb;
   int a_kblock;  // > 0: A is split along K into blocks of a_kblock columns (3-D tensor map {k, m, block})
-  int stream_out;  // 1: the output (and the fp32 residual it is read from) is much larger than L2 -> ld/st.global.cs
-                   // (evict-first), so that this one-touch traffic does not push the re-used A / W tiles out of L2
-                   // (ncu: 4.4 GB DRAM reads for 2.4 GB algorithmic on the 75600 x 5120 x 5120 residual GEMM)
+  int stream_out;  // 1 (MV_GEMM_STREAM=1): ld/st.global.cs (evict-first) for the output and the fp32 residual, so that
+                   // this one-touch traffic does not push the re-used A / W tiles out of L2 (ncu: 4.4 GB DRAM reads
+                   // for 2.4 GB algorithmic on the 75600 x 5120 x 5120 residual GEMM).  Measured neutral: off.
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
@@ -355,7 +356,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
   }
   // tile width: 256 unless that leaves SMs idle on a skinny problem (MV_GEMM_BN=64|256 forces one, for tests)
   const int num_m = (M + BM - 1) / BM;
-  int bn = (M <= 512 && num_m * ((N + 255) / 256) < 2 * sm_count()) ? 64 : 256;
+  int bn = (num_m == 1 && (N + 255) / 256 < sm_count()) ? 64 : 256;   // measured: M = 512 is faster on 256-wide tiles
   {
     static int forced = -1;
     if (forced < 0) {
@@ -384,14 +385,13 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
   p.num_tiles = p.num_m * p.num_n;
   p.num_kb = (K + BK - 1) / BK;
   p.a_kblock = a_kblock;
-  p.stream_out = (static_cast<int64_t>(M) * N * (f32_out ? 4 : 2) > (int64_t{96} << 20)) ? 1 : 0;
   {
-    static int forced = -1;   // MV_GEMM_STREAM=0|1 overrides (A/B measurements)
-    if (forced < 0) {
+    static int stream = -1;   // MV_GEMM_STREAM=1 turns the evict-first accesses on; measured neutral (+-3 %), default off
+    if (stream < 0) {
       const char* e = getenv("MV_GEMM_STREAM");
-      forced = e ? (atoi(e) ? 1 : 0) : 2;
+      stream = (e != nullptr && atoi(e) != 0) ? 1 : 0;
     }
-    if (forced != 2) p.stream_out = forced;
+    p.stream_out = stream;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return bn == 64 ? dispatch_gemm<64>(tmA, tmB, p, epilogue, st) : dispatch_gemm<256>(tmA, tmB, p, epilogue, st);

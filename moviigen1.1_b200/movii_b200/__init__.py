@@ -54,6 +54,7 @@ _SIGNATURES = {
                            _f32, _ptr],
     "mv_linear_f32_vec": [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _ptr],
     "mv_sinusoid_embed": [_ptr, _int, _ptr, _int, _ptr],
+    "mv_attention_fwd_trace": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr, _int, _ptr],
     "mv_t5_attention": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _int, _ptr],
     "mv_t5_rmsnorm": [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _f32, _ptr],
     "mv_embed_gather": [_ptr, _i64, _i64, _ptr, _ptr, _i64, _int, _int, _ptr],
@@ -436,4 +437,18 @@ def mul_bf16(a, b, out):
         assert t.dim() == 2 and t.stride(1) == 1 and t.shape == a.shape, n
     _call("mv_mul_bf16", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), a.shape[0], a.shape[1],
           _stream())
+    return out
+
+
+def attention_trace(q, k, v, out, trace, softmax_scale=None):
+    """Diagnostics: attention() on the 128-key-step kernel + clock64 stamps into trace (int64 [2, steps, 8], cuda)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+        assert t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1 and t.stride(1) == 128, n
+    _req(trace, torch.int64, "trace")
+    assert trace.dim() == 3 and trace.shape[0] == 2 and trace.shape[2] == 8 and trace.is_contiguous()
+    Lq, H, _ = q.shape
+    _call("mv_attention_fwd_trace", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+          Lq, k.shape[0], H, float(softmax_scale if softmax_scale is not None else 128 ** -0.5), _p(trace),
+          trace.shape[1], _stream())
     return out
