@@ -311,7 +311,7 @@ def main():
                     traffic = json.load(fh).get("%s_sp%d" % (args.workload, world))
             except Exception:
                 traffic = None
-        roof = {"bound": "tensor", "kernel": "attention_fwd_kernel (self-attention, Lq=%d Lk=%d H=%d)" % (Lq, Lk, Hh),
+        roof = {"bound": "tensor", "kernel": "mv_attention_fwd (self-attention, Lq=%d Lk=%d H=%d)" % (Lq, Lk, Hh),
                 "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops"], 4),
                 "traffic": traffic, "peak_source": pk["src"], "launches_timed": len(self_attn),
                 "avg_launch_ms": round(avg_ms, 4),

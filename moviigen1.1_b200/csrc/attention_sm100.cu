@@ -31,6 +31,7 @@ constexpr int kBKV = 64;            // keys per step
 constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
 constexpr int kDefaultEmu = 1;      // 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
+constexpr int kDefaultStale = 0;
 constexpr int kDefaultKStep = 64;    // MV_ATTN_KSTEP=128 selects the single-score-buffer / 128-key-step kernel below
 constexpr int kDefaultSkewNs = 0;
 constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
@@ -428,7 +429,7 @@ constexpr uint32_t kKVTileBytes2 = kBKV2 * kD * 2;     // 32 KB
 constexpr uint32_t kKVHalfBytes2 = kKVTileBytes2 / 2;  // [128 x 64] sub-tile
 constexpr uint32_t kAttnSmem2 = 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 1024 + 512;
 
-template <int EMU, bool PP, bool TRACE>
+template <int EMU, bool PP, bool TRACE, bool STALE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -602,6 +603,126 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     // may"; warpgroup 1 primes barrier 1 so that warpgroup 0 goes first
     if (PP && wg == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
+    if constexpr (STALE) {
+      // ---- stale-reference variant: the exponentials of step j use the reference (m_run) known BEFORE the step, so
+      // the row-max reduction is off the per-tile critical path (it runs in the shadow of the MUFU-bound exp pass
+      // and only feeds the NEXT step).  Exact: the reference is raised (O, l rescaled) at the start of the next
+      // step when the running max has grown by more than 2^8, and a step that meets a score more than 2^60 above
+      // its reference (never in practice) is redone with the true max before anything is stored.
+      float m_pend = -INFINITY;   // running row max seen so far (>= m_run)
+      const float inv_sl2 = 1.0f / sl2;
+      auto rescale_to = [&](float m_new) {
+        const float alpha = fast_exp2((m_run - m_new) * sl2);
+        l_run *= alpha;
+        m_run = m_new;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + c * 32, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(tO + c * 32, o);
+        }
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && lane == 0 && j < p.trace_steps;
+        unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
+        mbar_wait(&s_full[wg], j & 1);
+        if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);   // never blocks (see the classic loop); phases observed in order
+        tc_fence_after();
+        if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
+        if (j > 0) {
+          const bool need = (m_pend - m_run) * sl2 > 8.0f;
+          if (__any_sync(0xffffffffu, need)) rescale_to(m_pend);   // P.V(j-1) has landed: O is complete up to step j-1
+        }
+        uint32_t s[4][32];
+        const int valid = p.Lk - j * kBKV2;
+        auto load_scores = [&]() {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, s[c]);
+          tc_wait_ld();
+          if (valid < kBKV2) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+          }
+        };
+        load_scores();
+        if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
+        auto row_max = [&]() {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmax3(mx0, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]));
+              mx1 = fmax3(mx1, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
+            }
+          return fmaxf(mx0, mx1);
+        };
+        if (j == 0) {   // no reference yet: classic row max first
+          m_run = row_max();
+          m_pend = m_run;
+        }
+        if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
+        uint32_t pk[2][32];
+        float2 sum2;
+        float mxall;
+        bool redo;
+#pragma unroll 1
+        do {
+          const float neg_m = -m_run * sl2;
+          const float2 sc2 = make_float2(sl2, sl2);
+          const float2 nm2 = make_float2(neg_m, neg_m);
+          sum2 = make_float2(0.f, 0.f);
+          float mx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = h * 2 + cc;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+                const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+                float2 e01, e23;
+                e01.x = fast_exp2(x01.x);
+                e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
+                e23.x = fast_exp2(x23.x);
+                e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
+                // the row max is tracked on the exponentials themselves (monotonic in the scores: scale > 0), which
+                // are needed for the sum and the bf16 pack anyway — no second live copy of the row
+                mx[c] = fmax3(mx[c], e01.x, e01.y);
+                mx[c] = fmax3(mx[c], e23.x, e23.y);
+                sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
+                pk[h][cc * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+                pk[h][cc * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
+              }
+            }
+          }
+          const float emax = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], 1.0f);   // 2^((row max - m_run) * scale_log2), >= 1
+          mxall = fmaf(__log2f(emax), inv_sl2, m_run);                          // = max(row max, m_run) (inf if e overflowed)
+          redo = __any_sync(0xffffffffu, emax > 1.152921504606847e18f);        // 2^60 (also catches inf)
+          if (redo) {
+            load_scores();   // the scores are still in TMEM: P has not been stored yet
+            rescale_to(fmaxf(m_run, row_max()));   // exact reference; the second pass cannot overflow
+          }
+        } while (redo);
+        l_run += sum2.x + sum2.y;
+        m_pend = fmaxf(m_pend, mxall);
+        if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
+        tmem_st_x32(tS, pk[0]);
+        tmem_st_x32(tS + 32, pk[1]);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[wg]);
+        if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
+      }
+    } else {
     for (int j = 0; j < n_kv; ++j) {
       // S(j) complete implies P.V(j-1) complete (same issuing thread, in order, and its commit came first), so the
       // o_done wait below never blocks; it is taken every step so that every phase of the barrier is observed in order.
@@ -693,6 +814,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg]);
       if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
+    }
+
     }
 
     // ------------------------------ final epilogue ----------------------------
@@ -823,28 +946,41 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<2, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (kstep == 128 || p.trace != nullptr) {
-    if (p.trace != nullptr && p.pingpong) attention_fwd_k128_kernel<0, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else if (p.pingpong) attention_fwd_k128_kernel<0, true, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else if (emu == 2) attention_fwd_k128_kernel<2, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else if (emu == 1) attention_fwd_k128_kernel<1, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
-    else attention_fwd_k128_kernel<0, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    static int stale = -1;   // MV_ATTN_STALE=1: exponentials use the previous step's reference (row max off the critical path)
+    if (stale < 0) {
+      const char* e = getenv("MV_ATTN_STALE");
+      stale = e ? atoi(e) : kDefaultStale;
+    }
+    if (stale && !p.pingpong && emu == 0 && softmax_scale > 0.f) {
+      if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+      else attention_fwd_k128_kernel<0, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    } else
+    if (p.trace != nullptr && p.pingpong) attention_fwd_k128_kernel<0, true, true, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (p.pingpong) attention_fwd_k128_kernel<0, true, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 2) attention_fwd_k128_kernel<2, false, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 1) attention_fwd_k128_kernel<1, false, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+    else attention_fwd_k128_kernel<0, false, false, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
     MV_CHECK_LAUNCH("attention_fwd_k128_kernel");
     return MV_OK;
   }

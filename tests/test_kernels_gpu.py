@@ -108,6 +108,30 @@ def test_attention_strided_views_and_scale(mv):
     assert rel_l2(out.float(), ref) <= 5e-3
 
 
+@pytest.mark.parametrize("jumps", [(0.0, 0.3, 0.6, 0.9, 1.2, 1.5, 1.8, 2.1), (0.0, 0.0, 5.0, 5.0, 0.5, 12.0, 12.0, 1.0),
+                                   (3.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)])
+def test_attention_running_max_growth(mv, jumps):
+    """Online-softmax bookkeeping under a row max that keeps growing along the key axis: per 128-key block b every key
+    gets an extra score of 16.3 * jumps[b] in log2 units (q = ones, k += jumps[b] * ones).  Small steps exercise the
+    lazy (deferred) rescale of the accumulator, jumps of more than 2^60 the exact redo path of the stale-reference
+    kernel, a decreasing profile the no-rescale path.  Exact fp32 softmax reference."""
+    g = torch.Generator().manual_seed(19)
+    Lq, H = 256, 2
+    Lk = 128 * len(jumps) - 37                   # ragged last block
+    q = torch.ones(Lq, H, 128) + 0.05 * torch.randn(Lq, H, 128, generator=g)
+    k = 0.2 * torch.randn(Lk, H, 128, generator=g)
+    for b, c in enumerate(jumps):
+        k[128 * b + 5:128 * b + 9] += c        # a few keys per block carry the jump
+    v = torch.randn(Lk, H, 128, generator=g)
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    ref = O.attention(q, k, v, O.bf16_rt)
+    out = torch.full((Lq, H, 128), float("nan"), dtype=torch.bfloat16, device=DEV)
+    mv.attention(q.to(DEV), k.to(DEV), v.to(DEV), out)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) <= 5e-3
+
+
 # ---------------------------------------------------------------------------------------------- rowops
 @pytest.mark.parametrize("M,C", [(7, 128), (33, 5120), (5, 1536)])
 @pytest.mark.parametrize("variant", ["plain", "mod", "affine", "round_mod"])
