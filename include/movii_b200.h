@@ -199,6 +199,12 @@ int mv_attention_fwd_trace(const void* q, int64_t ldq, const void* k, int64_t ld
                            int64_t ldo, int Lq, int Lk, int H, float softmax_scale, unsigned long long* trace,
                            int trace_steps, mv_stream_t stream);
 
+/* Diagnostics only: overrides the attention kernel variant chosen from the environment (MV_ATTN_KSTEP / _EMU / _STALE /
+ * _PINGPONG / _SPLIT) for A/B timing inside one process; a negative argument keeps the current value.  kstep 64 | 128,
+ * emu 0..2 (fraction of exponentials on the FMA pipe: none, 1/4, 1/2), split 1 = two threads per query row.
+ * tools/ab_step.py. */
+int mv_attention_config(int kstep, int emu, int stale, int pingpong, int split);
+
 /* ---- umT5 text encoder (caller side of the hot path) --------------------------- */
 
 /* o[Lq,H,64] = softmax(q k^T + bias[h, (j - i) + bias_center] + key mask) v, no 1/sqrt(d) scaling, keys >= kv_len

@@ -30,9 +30,11 @@ constexpr int kBQ = 128;            // rows per Q tile
 constexpr int kBKV = 64;            // keys per step
 constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
-constexpr int kDefaultEmu = 1;      // 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
+constexpr int kDefaultEmu64 = 1;    // 64-key kernel: 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
+constexpr int kDefaultEmu128 = 0;   // 128-key kernel: MUFU only (the emulation lengthens the per-tile critical path: -18 %)
 constexpr int kDefaultStale = 0;
-constexpr int kDefaultKStep = 64;    // MV_ATTN_KSTEP=128 selects the single-score-buffer / 128-key-step kernel below
+constexpr int kDefaultSplit = 0;     // MV_ATTN_SPLIT=1: two threads per query row (attention_fwd_k128x2_kernel)
+constexpr int kDefaultKStep = 128;   // 128-key-step kernel below (in the 14B 720P step: 1019 vs 946 TF/s); MV_ATTN_KSTEP=64: the kernel above
 constexpr int kDefaultSkewNs = 0;
 constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
@@ -604,17 +606,21 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     if (PP && wg == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
     if constexpr (STALE) {
-      // ---- stale-reference variant: the exponentials of step j use the reference (m_run) known BEFORE the step, so
-      // the row-max reduction is off the per-tile critical path (it runs in the shadow of the MUFU-bound exp pass
-      // and only feeds the NEXT step).  Exact: the reference is raised (O, l rescaled) at the start of the next
-      // step when the running max has grown by more than 2^8, and a step that meets a score more than 2^60 above
-      // its reference (never in practice) is redone with the true max before anything is stored.
-      float m_pend = -INFINITY;   // running row max seen so far (>= m_run)
-      const float inv_sl2 = 1.0f / sl2;
-      auto rescale_to = [&](float m_new) {
-        const float alpha = fast_exp2((m_run - m_new) * sl2);
+      // ---- stale-reference variant (MV_ATTN_STALE=1): the exponentials of step j use the reference known BEFORE the
+      // step, and the row max is reduced in the shadow of the MUFU-bound exp pass — on the exponent arguments
+      // x = s * scale_log2 - ref, which exist anyway (no extra live registers), with max3 instructions that do not
+      // depend on the exponentials and issue on the ALU pipe between them — so it is off the per-tile critical
+      // path S -> P.  Exact: the reference is raised (O, l rescaled) at the start of the next step when the running
+      // max has grown by more than 2^8, and a step whose exponentials sum to more than 2^64 (a score ~2^57 above
+      // its reference: practically never) is redone from the scores still in TMEM with the true max before anything
+      // is stored.  All references are kept in scaled units (raw score * scale_log2).
+      float ref2 = 0.f;      // reference of the current exponentials, scaled: P = 2^(s * scale_log2 - ref2)
+      float grow = 0.f;      // how far the running row max (incl. the step just finished) is above ref2 (>= 0)
+      bool need = false;     // warp-uniform: some row of this warp must raise its reference before the next step
+      auto rescale_by = [&](float up) {   // ref2 += up (up >= 0); O and l follow
+        const float alpha = fast_exp2(-up);
         l_run *= alpha;
-        m_run = m_new;
+        ref2 += up;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
@@ -628,14 +634,13 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       for (int j = 0; j < n_kv; ++j) {
         const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && lane == 0 && j < p.trace_steps;
         unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
+        // P.V(j-1) completes before the scores of step j (same issuing thread, committed first): taking its phase
+        // FIRST keeps the (free) probe off the path between "scores ready" and the first tcgen05.ld
+        if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);
         mbar_wait(&s_full[wg], j & 1);
-        if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);   // never blocks (see the classic loop); phases observed in order
         tc_fence_after();
         if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
-        if (j > 0) {
-          const bool need = (m_pend - m_run) * sl2 > 8.0f;
-          if (__any_sync(0xffffffffu, need)) rescale_to(m_pend);   // P.V(j-1) has landed: O is complete up to step j-1
-        }
+        if (need) rescale_by(grow);   // P.V(j-1) has landed: O is complete up to step j-1
         uint32_t s[4][32];
         const int valid = p.Lk - j * kBKV2;
         auto load_scores = [&]() {
@@ -650,35 +655,31 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
           }
         };
+        auto row_max = [&]() {
+          float mx[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            mx[c] = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx[c] = fmax3(mx[c], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+          }
+          return fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], -INFINITY);
+        };
         load_scores();
         if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
-        auto row_max = [&]() {
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = fmax3(mx0, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]));
-              mx1 = fmax3(mx1, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
-            }
-          return fmaxf(mx0, mx1);
-        };
-        if (j == 0) {   // no reference yet: classic row max first
-          m_run = row_max();
-          m_pend = m_run;
-        }
+        if (j == 0) ref2 = row_max() * sl2;   // no reference yet: classic row max first
         if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
         uint32_t pk[2][32];
         float2 sum2;
-        float mxall;
+        float mx[4];
         bool redo;
 #pragma unroll 1
         do {
-          const float neg_m = -m_run * sl2;
           const float2 sc2 = make_float2(sl2, sl2);
-          const float2 nm2 = make_float2(neg_m, neg_m);
+          const float2 nm2 = make_float2(-ref2, -ref2);
           sum2 = make_float2(0.f, 0.f);
-          float mx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mx[c] = 0.f;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -690,29 +691,25 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
                 float2 e01, e23;
                 e01.x = fast_exp2(x01.x);
-                e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
+                e01.y = (EMU >= 2) ? exp2_emu(fminf(x01.y, 126.f)) : fast_exp2(x01.y);
                 e23.x = fast_exp2(x23.x);
-                e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
-                // the row max is tracked on the exponentials themselves (monotonic in the scores: scale > 0), which
-                // are needed for the sum and the bf16 pack anyway — no second live copy of the row
-                mx[c] = fmax3(mx[c], e01.x, e01.y);
-                mx[c] = fmax3(mx[c], e23.x, e23.y);
+                e23.y = (EMU >= 1) ? exp2_emu(fminf(x23.y, 126.f)) : fast_exp2(x23.y);
+                mx[c] = fmax3(mx[c], x01.x, x01.y);   // shadow row max (feeds the NEXT step)
+                mx[c] = fmax3(mx[c], x23.x, x23.y);
                 sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
                 pk[h][cc * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
                 pk[h][cc * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
               }
             }
           }
-          const float emax = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], 1.0f);   // 2^((row max - m_run) * scale_log2), >= 1
-          mxall = fmaf(__log2f(emax), inv_sl2, m_run);                          // = max(row max, m_run) (inf if e overflowed)
-          redo = __any_sync(0xffffffffu, emax > 1.152921504606847e18f);        // 2^60 (also catches inf)
+          // overflow guard on the sum (inf included; !(x <= t) also catches NaN)
+          redo = __any_sync(0xffffffffu, !(sum2.x + sum2.y <= 1.8446744073709552e19f));   // 2^64
           if (redo) {
-            load_scores();   // the scores are still in TMEM: P has not been stored yet
-            rescale_to(fmaxf(m_run, row_max()));   // exact reference; the second pass cannot overflow
+            load_scores();                                     // the scores are still in TMEM: P has not been stored yet
+            rescale_by(fmaxf(row_max() * sl2 - ref2, 0.f));    // exact reference; the second pass cannot overflow
           }
         } while (redo);
         l_run += sum2.x + sum2.y;
-        m_pend = fmaxf(m_pend, mxall);
         if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
         tmem_st_x32(tS, pk[0]);
         tmem_st_x32(tS + 32, pk[1]);
@@ -721,15 +718,18 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[wg]);
         if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
+        // in the shadow of this tile's P.V / Q.K^T: fold the shadow max, decide about the next step's rescale
+        grow = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], 0.f);
+        need = __any_sync(0xffffffffu, grow > 8.0f);
       }
     } else {
     for (int j = 0; j < n_kv; ++j) {
-      // S(j) complete implies P.V(j-1) complete (same issuing thread, in order, and its commit came first), so the
-      // o_done wait below never blocks; it is taken every step so that every phase of the barrier is observed in order.
+      // S(j) complete implies P.V(j-1) complete (same issuing thread, in order, and its commit came first); the o_done
+      // phase is taken every step so that every phase of the barrier is observed in order.
       const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && lane == 0 && j < p.trace_steps;
       unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
+      if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);   // completes before s_full(j): probed first, off the S -> ld path
       mbar_wait(&s_full[wg], j & 1);
-      if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);
       tc_fence_after();
       if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
       uint32_t s[4][32];
@@ -857,7 +857,379 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   }
 }
 
+
+// ================================================================================================================
+// Row-split variant of the 128-key-step kernel (MV_ATTN_SPLIT=1): the same TMEM / ring / MMA choreography, but TWO
+// threads per query row — 16 softmax warps: tile w = warps 4+8w .. 11+8w, the first four take keys 0..63 of the step,
+// the other four keys 64..127 (warp % 4 = TMEM lane quadrant for both).  Why: with the two Q tiles in antiphase only
+// ONE softmax warp per SM sub-partition is active at a time, and a lone in-order warp cannot keep the 4-lane MUFU pipe
+// full (tools/probe/softmax_pipe_probe.cu: 1233 clk per 128 exponentials alone vs 1043 clk with two warps sharing the
+// sub-partition); the row max, TMEM load, bf16 pack and P store of the step are halved per thread as well.  The two
+// half-row threads exchange their partial row max through shared memory (one 64-thread named barrier per step, which
+// also orders "partner has read its scores" before P overwrites them); partial row sums are combined once, in the
+// epilogue; each thread rescales / writes its own 64 columns of O.
+// ================================================================================================================
+constexpr int kAttnThreadsX2 = 640;
+constexpr uint32_t kXchBytes = 2 * 2 * 2 * kBQ * 4;   // [parity][tile][half][row] fp32
+constexpr uint32_t kAttnSmemX2 = kAttnSmem2 + kXchBytes;
+
+template <int EMU, bool TRACE>
+__global__ void __launch_bounds__(kAttnThreadsX2, 1)
+attention_fwd_k128x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                        // 2 tiles
+  uint8_t* sKV = smem + 2 * kQTileBytes;     // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2);
+  uint64_t* q_full = bars;                    // 1
+  uint64_t* kv_full = bars + 1;               // kKVStages2
+  uint64_t* kv_empty = kv_full + kKVStages2;  // kKVStages2
+  uint64_t* s_full = kv_empty + kKVStages2;   // [w] -> 2
+  uint64_t* p_full = s_full + 2;              // [w] -> 2
+  uint64_t* o_done = p_full + 2;              // [w] -> 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* xch = reinterpret_cast<float*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int n_kv = (p.Lk + kBKV2 - 1) / kBKV2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKVStages2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);  // released by both tiles' issuing warps
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);  // one arrive per softmax warp of the tile
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // register budget of the CTA pool: 640 x 96 at launch; the four producer warps give back 4 x 32 x 64 = 8192, which
+    // is exactly what the sixteen softmax warps need to go from 96 to 112 (setmaxnreg only moves registers inside the
+    // CTA's own allocation: asking for more than was released blocks for ever)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 0) {
+      // ------------------------------ TMA producer: Q, K_0, then V_j, K_{j+1} ------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kQTileBytes);
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_tile = [&](const CUtensorMap* tm, int j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[stage], kKVTileBytes2);
+          tma_load_3d(sKV + stage * kKVTileBytes2, tm, &kv_full[stage], 0, head, j * kBKV2);
+          tma_load_3d(sKV + stage * kKVTileBytes2 + kKVHalfBytes2, tm, &kv_full[stage], 64, head, j * kBKV2);
+        }
+        __syncwarp();
+        if (++stage == kKVStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      load_tile(&tmK, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        load_tile(&tmV, j);
+        if (j + 1 < n_kv) load_tile(&tmK, j + 1);
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ------------------------------ MMA issuers: one warp per Q tile (as in the kernel above) -------------
+      // Descriptors as (low, high) words: this warp runs on 32 registers (setmaxnreg.dec) so that the 16 softmax
+      // warps can have 112 each.
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kBQ, kBKV2, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
+      const int w = warp - 1;
+      const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ) + w * kQTileBytes);
+      const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV));
+      const uint64_t vdesc = make_desc_mnmajor_sw128(smem_u32(sKV), kKVHalfBytes2);
+      const uint32_t q_lo = static_cast<uint32_t>(qdesc), k_lo0 = static_cast<uint32_t>(kdesc), v_lo0 = static_cast<uint32_t>(vdesc);
+      const uint32_t qk_hi = static_cast<uint32_t>(kdesc >> 32), v_hi = static_cast<uint32_t>(vdesc >> 32);
+      const uint32_t tS = tmem_base + w * 128;
+      const uint32_t tO = tmem_base + 256 + w * 128;
+      auto issue_qk = [&](int st) {
+        const uint32_t k_lo = k_lo0 + st * (kKVTileBytes2 >> 4);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint32_t qo = ((k >> 2) * kQHalfBytes + (k & 3) * 32) >> 4;
+          const uint32_t ko = ((k >> 2) * kKVHalfBytes2 + (k & 3) * 32) >> 4;
+          umma_ss_lh(tS, q_lo + qo, qk_hi, k_lo + ko, qk_hi, idesc_qk, k != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int st, uint32_t acc) {
+        const uint32_t v_lo = v_lo0 + st * (kKVTileBytes2 >> 4);
+#pragma unroll
+        for (int k = 0; k < kBKV2 / 16; ++k) umma_ts_lh(tO, tS + k * 8, v_lo + ((k * 2048) >> 4), v_hi, idesc_pv, (acc | k) != 0 ? 1u : 0u);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kKVStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_qk(stage);
+        umma_commit(&s_full[w]);
+        umma_commit(&kv_empty[stage]);
+      }
+      __syncwarp();
+      advance();
+      for (int j = 0; j < n_kv; ++j) {
+        const int vstage = stage;
+        const uint32_t vphase = phase;
+        advance();
+        const bool more = (j + 1 < n_kv);
+        const int kstage = stage;
+        const uint32_t kphase = phase;
+        if (more) advance();
+        mbar_wait(&kv_full[vstage], vphase);
+        if (more) mbar_wait(&kv_full[kstage], kphase);
+        mbar_wait(&p_full[w], j & 1);
+        tc_fence_after();
+        if constexpr (TRACE) {
+          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
+            p.trace[(w * p.trace_steps + j) * 8 + 5] = clock64();
+        }
+        if (elect_one()) {
+          issue_pv(vstage, j > 0 ? 1u : 0u);
+          umma_commit(&o_done[w]);
+          umma_commit(&kv_empty[vstage]);
+          if (more) {
+            issue_qk(kstage);   // in issue order behind P.V(j): overwrites the S/P buffer only after P was read
+            umma_commit(&s_full[w]);
+            umma_commit(&kv_empty[kstage]);
+          }
+        }
+        __syncwarp();
+        if constexpr (TRACE) {
+          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
+            p.trace[(w * p.trace_steps + j) * 8 + 6] = clock64();
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ------------------------------ softmax: 2 tiles x 2 key halves x 4 lane quadrants ------------------------
+    const int sw = warp - 4;
+    const int wg = sw >> 3;          // Q tile
+    const int hf = (sw >> 2) & 1;    // key half of every step (and column half of O)
+    const int quad = warp & 3;       // TMEM lane quadrant
+    const int rloc = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + wg * 128 + hf * 64;        // this thread's 64 scores
+    const uint32_t tP = tmem_base + lane_base + wg * 128 + hf * 32;        // its 32 packed-bf16 columns of P
+    const uint32_t tO = tmem_base + lane_base + 256 + wg * 128 + hf * 64;  // its 64 columns of O
+    const float sl2 = p.scale_log2;
+    const int bar_id = 1 + wg * 4 + quad;   // named barrier of the two warps that share these 32 rows
+    float* xmine = xch + (wg * 2 + hf) * kBQ + rloc;
+    float* xpeer = xch + (wg * 2 + (hf ^ 1)) * kBQ + rloc;
+    float m_run = -INFINITY;   // running row max of raw scores (identical in both threads of a row)
+    float l_run = 0.f;         // row sum over THIS thread's keys
+
+    for (int j = 0; j < n_kv; ++j) {
+      const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && hf == 0 && lane == 0 && j < p.trace_steps;
+      unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
+      if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);   // completes before s_full(j); every phase observed in order
+      mbar_wait(&s_full[wg], j & 1);
+      tc_fence_after();
+      if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
+      uint32_t s[2][32];
+      tmem_ld_x32(tS, s[0]);
+      tmem_ld_x32(tS + 32, s[1]);
+      tc_wait_ld();
+      if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
+      const int valid = p.Lk - j * kBKV2 - hf * 64;
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+      }
+      float mx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx[c] = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          mx[c] = fmax3(mx[c], __uint_as_float(s[c >> 1][(c & 1) * 16 + i]), __uint_as_float(s[c >> 1][(c & 1) * 16 + i + 1]));
+      }
+      const float m_loc = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], -INFINITY);
+      // exchange with the thread that holds the other 64 keys of this row.  The barrier also guarantees that the
+      // partner's scores are in its registers before this thread's P overwrites them (P of keys 64..127 lands on the
+      // columns that held the scores of keys 32..63).
+      float* xw = xmine + (j & 1) * (4 * kBQ);
+      *xw = m_loc;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      const float m_new = fmax3(m_run, m_loc, xpeer[(j & 1) * (4 * kBQ)]);
+      if (j == 0) {
+        m_run = m_new;
+      } else {
+        const bool need = (m_new - m_run) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {   // same rows, same values: both warps of the pair take the same branch
+          const float alpha = fast_exp2((m_run - m_new) * sl2);
+          l_run *= alpha;
+          m_run = m_new;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + c * 32, o);
+          }
+        }
+      }
+      if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
+      const float neg_m = -m_run * sl2;
+      const float2 sc2 = make_float2(sl2, sl2);
+      const float2 nm2 = make_float2(neg_m, neg_m);
+      float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+          const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+          float2 e01, e23;
+          e01.x = fast_exp2(x01.x);
+          e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
+          e23.x = fast_exp2(x23.x);
+          e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
+          sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
+          pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+          pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
+        }
+      }
+      l_run += sum2.x + sum2.y;
+      if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
+      tmem_st_x32(tP, pk);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[wg]);
+      if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
+    }
+
+    // ------------------------------ final epilogue ----------------------------
+    mbar_wait(&o_done[wg], (n_kv - 1) & 1);
+    tc_fence_after();
+    {   // total row sum = this thread's keys + the partner's (parity slot of step n_kv: never in use by step n_kv - 1)
+      float* xw = xmine + (n_kv & 1) * (4 * kBQ);
+      *xw = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      l_run += xpeer[(n_kv & 1) * (4 * kBQ)];
+    }
+    const float inv_l = 1.0f / l_run;
+    const int row = q0 + wg * kBQ + rloc;
+    __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * kD + hf * 64;
+    if (p.n_dst > 0 && row < p.Lq) {
+      const int dst = row / p.rows_per_rank;
+      const int rl = row - dst * p.rows_per_rank;
+      orow = p.o_dst[dst] + (static_cast<int64_t>(p.src_rank) * p.rows_per_rank + rl) * p.ldo + head * kD + hf * 64;
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_x32(tO + c * 32, o);
+      tc_wait_ld();
+      if (row < p.Lq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          dst[i] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace mv
+
+// Kernel-variant knobs: environment defaults (read once), overridable at run time through mv_attention_config
+// (A/B measurements inside one process; the product path never calls it).
+namespace {
+struct AttnKnobs {
+  int kstep, emu, stale, pingpong, order, skew, split;
+  bool init;
+};
+AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, 0, false};
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+}
+AttnKnobs& attn_knobs() {
+  if (!g_knobs.init) {
+    const int ks = env_int("MV_ATTN_KSTEP", mv::kDefaultKStep);
+    g_knobs.kstep = (ks == 128 || ks == 64) ? ks : mv::kDefaultKStep;
+    const int emu_dflt = g_knobs.kstep == 128 ? mv::kDefaultEmu128 : mv::kDefaultEmu64;
+    const int em = env_int("MV_ATTN_EMU", emu_dflt);
+    g_knobs.emu = (em >= 0 && em <= 2) ? em : emu_dflt;
+    g_knobs.stale = env_int("MV_ATTN_STALE", mv::kDefaultStale);
+    g_knobs.pingpong = env_int("MV_ATTN_PINGPONG", mv::kDefaultPingPong);
+    g_knobs.order = env_int("MV_ATTN_ORDER", 0) == 1 ? 1 : 0;   // default 0: same speed since each tile has its own issuer
+    g_knobs.skew = env_int("MV_ATTN_SKEW", mv::kDefaultSkewNs);
+    g_knobs.split = env_int("MV_ATTN_SPLIT", mv::kDefaultSplit) != 0 ? 1 : 0;
+    g_knobs.init = true;
+  }
+  return g_knobs;
+}
+}  // namespace
+
+extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int split) {
+  AttnKnobs& kn = attn_knobs();
+  if ((kstep >= 0 && kstep != 64 && kstep != 128) || emu > 2) {
+    mv::set_error("mv_attention_config: kstep must be 64 or 128, emu 0..2 (negative = keep)");
+    return MV_E_SHAPE;
+  }
+  if (kstep >= 0) kn.kstep = kstep;
+  if (emu >= 0) kn.emu = emu;
+  if (stale >= 0) kn.stale = stale;
+  if (pingpong >= 0) kn.pingpong = pingpong;
+  if (split >= 0) kn.split = split != 0 ? 1 : 0;
+  return MV_OK;
+}
 
 static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                           int64_t ldo, int Lq, int Lk, int H, float softmax_scale, void* const* o_dst, int n_dst,
@@ -883,11 +1255,8 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
     return make_tmap_bf16(tm, base, 3, dims, str, box, true);
   };
-  static int kstep = -1;   // keys per softmax step: 64 (double-buffered scores) or 128 (MV_ATTN_KSTEP overrides)
-  if (kstep < 0) {
-    const char* e = getenv("MV_ATTN_KSTEP");
-    kstep = (e != nullptr && atoi(e) == 128) ? 128 : ((e != nullptr && atoi(e) == 64) ? 64 : kDefaultKStep);
-  }
+  const AttnKnobs& kn = attn_knobs();
+  const int kstep = kn.kstep;   // keys per softmax step: 64 (double-buffered scores) or 128
   if ((rc = mk(&tmQ, q, ldq, Lq, kBQ)) != MV_OK) return rc;
   if ((rc = mk(&tmK, k, ldk, Lk, kstep)) != MV_OK) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, kstep)) != MV_OK) return rc;
@@ -899,26 +1268,9 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   p.Lk = Lk;
   p.n_kv = (Lk + kBKV - 1) / kBKV;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  {
-    static int order = -1;
-    if (order < 0) {
-      const char* e = getenv("MV_ATTN_ORDER");
-      order = (e != nullptr && e[0] == '1') ? 1 : 0;   // default 0: same speed since each tile has its own issuer
-    }
-    p.order = order;
-    static int skew = -1;
-    if (skew < 0) {
-      const char* e = getenv("MV_ATTN_SKEW");
-      skew = e ? atoi(e) : kDefaultSkewNs;
-    }
-    p.skew_ns = skew;
-    static int pp = -1;
-    if (pp < 0) {
-      const char* e = getenv("MV_ATTN_PINGPONG");
-      pp = e ? atoi(e) : kDefaultPingPong;
-    }
-    p.pingpong = pp;
-  }
+  p.order = kn.order;
+  p.skew_ns = kn.skew;
+  p.pingpong = kn.pingpong;
   p.trace = trace;
   p.trace_steps = trace_steps;
   p.n_dst = n_dst;
@@ -936,10 +1288,10 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   }
 
   // fraction of exponentials evaluated on the FMA pipe: 0 = none, 1 = 1/4, 2 = 1/2 (MV_ATTN_EMU overrides)
-  static int emu = -1;
-  if (emu < 0) {
-    const char* e = getenv("MV_ATTN_EMU");
-    emu = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : kDefaultEmu;
+  const int emu = kn.emu;
+  static bool attr_done = false;
+  if (!attr_done) {
+    attr_done = true;
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -962,17 +1314,32 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem2)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmemX2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmemX2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmemX2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmemX2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((kstep == 128 || p.trace != nullptr) && kn.split) {
+    if (p.trace != nullptr) attention_fwd_k128x2_kernel<0, true><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 2) attention_fwd_k128x2_kernel<2, false><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu == 1) attention_fwd_k128x2_kernel<1, false><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else attention_fwd_k128x2_kernel<0, false><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    MV_CHECK_LAUNCH("attention_fwd_k128x2_kernel");
+    return MV_OK;
+  }
   if (kstep == 128 || p.trace != nullptr) {
-    static int stale = -1;   // MV_ATTN_STALE=1: exponentials use the previous step's reference (row max off the critical path)
-    if (stale < 0) {
-      const char* e = getenv("MV_ATTN_STALE");
-      stale = e ? atoi(e) : kDefaultStale;
-    }
-    if (stale && !p.pingpong && emu == 0 && softmax_scale > 0.f) {
+    const int stale = kn.stale;   // 1: exponentials use the previous step's reference (row max off the critical path)
+    if (stale && !p.pingpong && emu <= 1 && softmax_scale > 0.f) {
       if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+      else if (emu == 1) attention_fwd_k128_kernel<1, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else attention_fwd_k128_kernel<0, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
     } else
     if (p.trace != nullptr && p.pingpong) attention_fwd_k128_kernel<0, true, true, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);

@@ -93,6 +93,32 @@ def test_attention(mv, Lq, Lk, H):
     assert (out.float().cpu() - ref).abs().max().item() <= 2e-2
 
 
+@pytest.mark.parametrize("Lq,Lk,H,n_dst", [(301, 333, 2, 2), (1024, 512, 3, 4)])
+def test_attention_scatter_epilogue(mv, Lq, Lk, H, n_dst):
+    """mv_attention_fwd_scatter (the fused Ulysses return path): query row r is stored into destination
+    r // rows_per_rank at [src_rank][r % rows_per_rank][H*128].  The destinations are local buffers here (on a
+    multi-GPU box they are the peers' IPC-mapped slabs, tests/test_sp_multigpu.py)."""
+    g = torch.Generator().manual_seed(Lq + Lk + H)
+    q = torch.randn(Lq, H, 128, generator=g).bfloat16()
+    k = torch.randn(Lk, H, 128, generator=g).bfloat16()
+    v = torch.randn(Lk, H, 128, generator=g).bfloat16()
+    ref = O.attention(q, k, v, O.bf16_rt)
+    rows = (Lq + n_dst - 1) // n_dst
+    src_rank = n_dst - 1
+    dsts = [torch.full((n_dst, rows, H * 128), float("nan"), dtype=torch.bfloat16, device=DEV) for _ in range(n_dst)]
+    tab = mv.ptr_table([d.data_ptr() for d in dsts])
+    mv.attention_scatter(q.to(DEV), k.to(DEV), v.to(DEV), tab, n_dst, src_rank, rows, H * 128)
+    torch.cuda.synchronize()
+    got = torch.cat([d[src_rank] for d in dsts], 0)[:Lq].view(Lq, H, 128).float().cpu()
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) <= 5e-3
+    for d in dsts:   # nothing but the src_rank slab (and only its valid rows) was written
+        other = torch.cat([d[:src_rank], d[src_rank + 1:]], 0)
+        assert torch.isnan(other.float()).all()
+    tail = dsts[-1][src_rank][Lq - (n_dst - 1) * rows:]
+    assert torch.isnan(tail.float()).all()
+
+
 def test_attention_strided_views_and_scale(mv):
     """q/k/v as column slices of one fused [L, 3*H*128] QKV buffer (how the DiT block calls it), sharp softmax."""
     g = torch.Generator().manual_seed(11)
@@ -110,10 +136,11 @@ def test_attention_strided_views_and_scale(mv):
 
 @pytest.mark.parametrize("jumps", [(0.0, 0.3, 0.6, 0.9, 1.2, 1.5, 1.8, 2.1), (0.0, 0.0, 5.0, 5.0, 0.5, 12.0, 12.0, 1.0),
                                    (3.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)])
-def test_attention_running_max_growth(mv, jumps):
+@pytest.mark.parametrize("offset", [5, 70])
+def test_attention_running_max_growth(mv, jumps, offset):
     """Online-softmax bookkeeping under a row max that keeps growing along the key axis: per 128-key block b every key
     gets an extra score of 16.3 * jumps[b] in log2 units (q = ones, k += jumps[b] * ones).  Small steps exercise the
-    lazy (deferred) rescale of the accumulator, jumps of more than 2^60 the exact redo path of the stale-reference
+    lazy (deferred) rescale of the accumulator, jumps of more than 2^64 the exact redo path of the stale-reference
     kernel, a decreasing profile the no-rescale path.  Exact fp32 softmax reference."""
     g = torch.Generator().manual_seed(19)
     Lq, H = 256, 2
@@ -121,7 +148,7 @@ def test_attention_running_max_growth(mv, jumps):
     q = torch.ones(Lq, H, 128) + 0.05 * torch.randn(Lq, H, 128, generator=g)
     k = 0.2 * torch.randn(Lk, H, 128, generator=g)
     for b, c in enumerate(jumps):
-        k[128 * b + 5:128 * b + 9] += c        # a few keys per block carry the jump
+        k[128 * b + offset:128 * b + offset + 4] += c        # a few keys per block carry the jump (first / second half)
     v = torch.randn(Lk, H, 128, generator=g)
     q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
     ref = O.attention(q, k, v, O.bf16_rt)
