@@ -32,7 +32,8 @@ constexpr int kKVStages = 8;        // ring of 16 KB tiles
 constexpr int kAttnThreads = 384;
 constexpr int kDefaultEmu64 = 1;    // 64-key kernel: 1/4 of the exponentials on the FMA pipe (+5.7 % measured, 1172 -> 1239 TF/s)
 constexpr int kDefaultEmu128 = 0;   // 128-key kernel: MUFU only (the emulation lengthens the per-tile critical path: -18 %)
-constexpr int kDefaultStale = 0;
+constexpr int kDefaultStale = 1;     // 128-key kernel: fixed-reference softmax (no per-step row max): 1371 vs 1209 TF/s alone,
+                                     // 1137 vs 1067 TF/s inside the power-capped 720P step; MV_ATTN_STALE=0: classic online softmax
 constexpr int kDefaultSplit = 0;     // MV_ATTN_SPLIT=1: two threads per query row (attention_fwd_k128x2_kernel)
 constexpr int kDefaultKStep = 128;   // 128-key-step kernel below (in the 14B 720P step: 1019 vs 946 TF/s); MV_ATTN_KSTEP=64: the kernel above
 constexpr int kDefaultSkewNs = 0;
@@ -606,17 +607,16 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     if (PP && wg == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
     if constexpr (STALE) {
-      // ---- stale-reference variant (MV_ATTN_STALE=1): the exponentials of step j use the reference known BEFORE the
-      // step, and the row max is reduced in the shadow of the MUFU-bound exp pass — on the exponent arguments
-      // x = s * scale_log2 - ref, which exist anyway (no extra live registers), with max3 instructions that do not
-      // depend on the exponentials and issue on the ALU pipe between them — so it is off the per-tile critical
-      // path S -> P.  Exact: the reference is raised (O, l rescaled) at the start of the next step when the running
-      // max has grown by more than 2^8, and a step whose exponentials sum to more than 2^64 (a score ~2^57 above
-      // its reference: practically never) is redone from the scores still in TMEM with the true max before anything
-      // is stored.  All references are kept in scaled units (raw score * scale_log2).
-      float ref2 = 0.f;      // reference of the current exponentials, scaled: P = 2^(s * scale_log2 - ref2)
-      float grow = 0.f;      // how far the running row max (incl. the step just finished) is above ref2 (>= 0)
-      bool need = false;     // warp-uniform: some row of this warp must raise its reference before the next step
+      // ---- fixed-reference variant (MV_ATTN_STALE=1): NO per-step row max.  The exponentials use a reference that is
+      // only moved when it has to be: P = 2^(s * scale_log2 - ref2) is exact for any ref2 as long as nothing
+      // overflows (bf16 P and the fp32 sums keep their relative precision at every magnitude; terms that underflow
+      // are below 2^-126 of the row's largest weight), so the lazy-rescale threshold of the classic loop (2^8) can
+      // be pushed to "when the step's exponentials sum to more than 2^64".  That test needs only the row sum, which
+      // exists anyway: the row-max instructions (1/6 of the softmax instruction count), the rescale vote and the
+      // max -> exp dependency are gone from the steady state.  A step that trips the test (a score ~2^57 above the
+      // reference; step 0 sets the reference to its exact row max) is redone from the scores still in TMEM with
+      // its true max, O and l rescaled, before anything is stored.  References are kept in scaled units.
+      float ref2 = 0.f;      // P = 2^(s * scale_log2 - ref2)
       auto rescale_by = [&](float up) {   // ref2 += up (up >= 0); O and l follow
         const float alpha = fast_exp2(-up);
         l_run *= alpha;
@@ -640,7 +640,6 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         mbar_wait(&s_full[wg], j & 1);
         tc_fence_after();
         if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
-        if (need) rescale_by(grow);   // P.V(j-1) has landed: O is complete up to step j-1
         uint32_t s[4][32];
         const int valid = p.Lk - j * kBKV2;
         auto load_scores = [&]() {
@@ -667,19 +666,16 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         };
         load_scores();
         if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
-        if (j == 0) ref2 = row_max() * sl2;   // no reference yet: classic row max first
+        if (j == 0) ref2 = row_max() * sl2;   // the first step fixes the reference at its exact row max
         if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
         uint32_t pk[2][32];
         float2 sum2;
-        float mx[4];
         bool redo;
 #pragma unroll 1
         do {
           const float2 sc2 = make_float2(sl2, sl2);
           const float2 nm2 = make_float2(-ref2, -ref2);
           sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) mx[c] = 0.f;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -694,8 +690,6 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 e01.y = (EMU >= 2) ? exp2_emu(fminf(x01.y, 126.f)) : fast_exp2(x01.y);
                 e23.x = fast_exp2(x23.x);
                 e23.y = (EMU >= 1) ? exp2_emu(fminf(x23.y, 126.f)) : fast_exp2(x23.y);
-                mx[c] = fmax3(mx[c], x01.x, x01.y);   // shadow row max (feeds the NEXT step)
-                mx[c] = fmax3(mx[c], x23.x, x23.y);
                 sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
                 pk[h][cc * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
                 pk[h][cc * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
@@ -718,9 +712,6 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[wg]);
         if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
-        // in the shadow of this tile's P.V / Q.K^T: fold the shadow max, decide about the next step's rescale
-        grow = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], 0.f);
-        need = __any_sync(0xffffffffu, grow > 8.0f);
       }
     } else {
     for (int j = 0; j < n_kv; ++j) {
@@ -873,7 +864,7 @@ constexpr int kAttnThreadsX2 = 640;
 constexpr uint32_t kXchBytes = 2 * 2 * 2 * kBQ * 4;   // [parity][tile][half][row] fp32
 constexpr uint32_t kAttnSmemX2 = kAttnSmem2 + kXchBytes;
 
-template <int EMU, bool TRACE>
+template <int EMU, bool TRACE, bool FIXREF>
 __global__ void __launch_bounds__(kAttnThreadsX2, 1)
 attention_fwd_k128x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -1050,8 +1041,21 @@ attention_fwd_k128x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int bar_id = 1 + wg * 4 + quad;   // named barrier of the two warps that share these 32 rows
     float* xmine = xch + (wg * 2 + hf) * kBQ + rloc;
     float* xpeer = xch + (wg * 2 + (hf ^ 1)) * kBQ + rloc;
-    float m_run = -INFINITY;   // running row max of raw scores (identical in both threads of a row)
+    float m_run = -INFINITY;   // classic: running row max of raw scores (identical in both threads of a row)
+    float ref2 = 0.f;          // fixed-reference: P = 2^(s * scale_log2 - ref2) (identical in both threads of a row)
     float l_run = 0.f;         // row sum over THIS thread's keys
+    auto rescale_o = [&](float alpha) {   // this thread's 64 columns of O
+      l_run *= alpha;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + c * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_x32(tO + c * 32, o);
+      }
+    };
 
     for (int j = 0; j < n_kv; ++j) {
       const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && hf == 0 && lane == 0 && j < p.trace_steps;
@@ -1061,74 +1065,100 @@ attention_fwd_k128x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       tc_fence_after();
       if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
       uint32_t s[2][32];
-      tmem_ld_x32(tS, s[0]);
-      tmem_ld_x32(tS + 32, s[1]);
-      tc_wait_ld();
-      if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
       const int valid = p.Lk - j * kBKV2 - hf * 64;
-      if (valid < 64) {
+      auto load_scores = [&]() {
+        tmem_ld_x32(tS, s[0]);
+        tmem_ld_x32(tS + 32, s[1]);
+        tc_wait_ld();
+        if (valid < 64) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-      }
-      float mx[4];
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+        }
+      };
+      auto local_max = [&]() {
+        float mx[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        mx[c] = -INFINITY;
+        for (int c = 0; c < 4; ++c) {
+          mx[c] = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 16; i += 2)
-          mx[c] = fmax3(mx[c], __uint_as_float(s[c >> 1][(c & 1) * 16 + i]), __uint_as_float(s[c >> 1][(c & 1) * 16 + i + 1]));
-      }
-      const float m_loc = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], -INFINITY);
-      // exchange with the thread that holds the other 64 keys of this row.  The barrier also guarantees that the
-      // partner's scores are in its registers before this thread's P overwrites them (P of keys 64..127 lands on the
-      // columns that held the scores of keys 32..63).
-      float* xw = xmine + (j & 1) * (4 * kBQ);
-      *xw = m_loc;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      const float m_new = fmax3(m_run, m_loc, xpeer[(j & 1) * (4 * kBQ)]);
-      if (j == 0) {
-        m_run = m_new;
-      } else {
-        const bool need = (m_new - m_run) * sl2 > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {   // same rows, same values: both warps of the pair take the same branch
-          const float alpha = fast_exp2((m_run - m_new) * sl2);
-          l_run *= alpha;
-          m_run = m_new;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_x32(tO + c * 32, o);
-            tc_wait_ld();
+          for (int i = 0; i < 16; i += 2)
+            mx[c] = fmax3(mx[c], __uint_as_float(s[c >> 1][(c & 1) * 16 + i]), __uint_as_float(s[c >> 1][(c & 1) * 16 + i + 1]));
+        }
+        return fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], -INFINITY);
+      };
+      // pair exchange through shared memory: publish `mine`, meet the partner (64-thread named barrier), read its value.
+      // Slots are double-buffered by `slot` parity: a slot is rewritten two exchanges later, i.e. after a barrier that the
+      // partner only passes once it has read the previous value.
+      auto exchange = [&](float mine, int slot) {
+        xmine[slot * (4 * kBQ)] = mine;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        return xpeer[slot * (4 * kBQ)];
+      };
+      float2 sum2;
+      uint32_t pk[32];
+      auto exp_pass = [&](float neg_ref) {   // pk = bf16(2^(s * scale_log2 + neg_ref)), sum2 = their fp32 sums
+        const float2 sc2 = make_float2(sl2, sl2);
+        const float2 nm2 = make_float2(neg_ref, neg_ref);
+        sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x32(tO + c * 32, o);
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+            const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+            float2 e01, e23;
+            e01.x = fast_exp2(x01.x);
+            e01.y = (EMU >= 2) ? exp2_emu(FIXREF ? fminf(x01.y, 126.f) : x01.y) : fast_exp2(x01.y);
+            e23.x = fast_exp2(x23.x);
+            e23.y = (EMU >= 1) ? exp2_emu(FIXREF ? fminf(x23.y, 126.f) : x23.y) : fast_exp2(x23.y);
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
+            pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+            pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
           }
         }
-      }
-      if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
-      const float neg_m = -m_run * sl2;
-      const float2 sc2 = make_float2(sl2, sl2);
-      const float2 nm2 = make_float2(neg_m, neg_m);
-      float2 sum2 = make_float2(0.f, 0.f);
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-          const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-          float2 e01, e23;
-          e01.x = fast_exp2(x01.x);
-          e01.y = (EMU >= 2) ? exp2_emu(x01.y) : fast_exp2(x01.y);
-          e23.x = fast_exp2(x23.x);
-          e23.y = (EMU >= 1) ? exp2_emu(x23.y) : fast_exp2(x23.y);
-          sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
-          pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
-          pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
+      };
+      load_scores();
+      if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
+      if constexpr (FIXREF) {
+        // ---- fixed reference (see the 128-key kernel above): no row max in the steady state.  Per step the pair meets
+        // once, right before the P stores, to (a) agree whether either half overflowed (then both redo the step with
+        // the exact row max) and (b) order "partner's scores are in its registers" before P overwrites them.
+        if (j == 0) ref2 = fmaxf(local_max(), exchange(local_max(), 0)) * sl2;   // exact row max of the first step
+        if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
+        exp_pass(-ref2);
+        const float ovf = __any_sync(0xffffffffu, !(sum2.x + sum2.y <= 1.8446744073709552e19f)) ? 1.f : 0.f;   // 2^64
+        const float peer_ovf = exchange(ovf, (j + 1) & 1);   // (step 0 used slot 0 for the row max)
+        if (ovf + peer_ovf != 0.f) {   // same for all 64 threads of the pair (the flags are warp-uniform)
+          load_scores();               // nothing has been stored yet: the scores are still in TMEM
+          const float m_loc = local_max();
+          const float m_row = fmaxf(m_loc, exchange(m_loc, j & 1));   // (also: both halves have re-read their scores)
+          // the next regular exchange re-uses this slot: make sure the partner has read it before moving on
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          const float up = fmaxf(m_row * sl2 - ref2, 0.f);
+          rescale_o(fast_exp2(-up));   // P.V(j-1) has landed (o_done probed above)
+          ref2 += up;
+          exp_pass(-ref2);             // exact reference: cannot overflow
         }
+      } else {
+        const float m_loc = local_max();
+        // exchange with the thread that holds the other 64 keys of this row.  The barrier also guarantees that the
+        // partner's scores are in its registers before this thread's P overwrites them (P of keys 64..127 lands on the
+        // columns that held the scores of keys 32..63).
+        const float m_new = fmax3(m_run, m_loc, exchange(m_loc, j & 1));
+        if (j == 0) {
+          m_run = m_new;
+        } else {
+          const bool need = (m_new - m_run) * sl2 > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {   // same rows, same values: both warps of the pair take the same branch
+            rescale_o(fast_exp2((m_run - m_new) * sl2));
+            m_run = m_new;
+          }
+        }
+        if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
+        exp_pass(-m_run * sl2);
       }
       l_run += sum2.x + sum2.y;
       if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
@@ -1143,11 +1173,11 @@ attention_fwd_k128x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     // ------------------------------ final epilogue ----------------------------
     mbar_wait(&o_done[wg], (n_kv - 1) & 1);
     tc_fence_after();
-    {   // total row sum = this thread's keys + the partner's (parity slot of step n_kv: never in use by step n_kv - 1)
-      float* xw = xmine + (n_kv & 1) * (4 * kBQ);
-      *xw = l_run;
+    {   // total row sum = this thread's keys + the partner's, through the slot the last step did NOT use
+      const int slot = FIXREF ? ((n_kv + 1) & 1) : (n_kv & 1);
+      xmine[slot * (4 * kBQ)] = l_run;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      l_run += xpeer[(n_kv & 1) * (4 * kBQ)];
+      l_run += xpeer[slot * (4 * kBQ)];
     }
     const float inv_l = 1.0f / l_run;
     const int row = q0 + wg * kBQ + rloc;
@@ -1316,22 +1346,30 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem2)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmemX2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmemX2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmemX2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((kstep == 128 || p.trace != nullptr) && kn.split) {
-    if (p.trace != nullptr) attention_fwd_k128x2_kernel<0, true><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else if (emu == 2) attention_fwd_k128x2_kernel<2, false><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else if (emu == 1) attention_fwd_k128x2_kernel<1, false><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else attention_fwd_k128x2_kernel<0, false><<<grid, kAttnThreadsX2, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    const bool fix = kn.stale != 0 && softmax_scale > 0.f;
+    const dim3 blk(kAttnThreadsX2);
+    if (p.trace != nullptr && fix) attention_fwd_k128x2_kernel<0, true, true><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else if (p.trace != nullptr) attention_fwd_k128x2_kernel<0, true, false><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else if (fix && emu >= 1) attention_fwd_k128x2_kernel<1, false, true><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else if (fix) attention_fwd_k128x2_kernel<0, false, true><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else if (emu >= 1) attention_fwd_k128x2_kernel<1, false, false><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
+    else attention_fwd_k128x2_kernel<0, false, false><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
     MV_CHECK_LAUNCH("attention_fwd_k128x2_kernel");
     return MV_OK;
   }
