@@ -1,7 +1,7 @@
 """In-step A/B of the attention kernel variants on the real 14B 720P forward (one process, one model build).
 For every variant: 1 untimed forward, then 2 timed forwards (= the DiT part of one denoising step) with per-launch
 CUDA-event timing of the self-attention kernel; SM clock / power sampled with nvidia-smi while timing.
-Usage: python tools/ab_step.py [workload] [variant ...]   variant = kstep:emu:stale:pingpong[:split]  (default list below)"""
+Usage: python tools/ab_step.py [workload] [variant ...]   variant = kstep:emu:stale:pingpong[:split[:skew]]  (default list below)"""
 import json
 import os
 import sys
@@ -41,8 +41,8 @@ def main():
     t = torch.tensor([900], device=dev)
     ref = None
     for var in variants:
-        ks, emu, stale, pp, split = (int(x) for x in (var.split(":") + ["0"])[:5])
-        mv.attention_config(ks, emu, stale, pp, split)
+        ks, emu, stale, pp, split, skew = (int(x) for x in (var.split(":") + ["0", "0"])[:6])
+        mv.attention_config(ks, emu, stale, pp, split, skew)
         out = model([lat], t=t, context=ctx, seq_len=seq_len)[0]
         torch.cuda.synchronize()
         sampler = bench.ClockSampler(0)
