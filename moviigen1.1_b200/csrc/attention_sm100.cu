@@ -1,9 +1,32 @@
 // Flash-attention forward for the DiT (head_dim 128, bf16, non-causal) on tcgen05 / TMEM / TMA.
+// Replaces flash_attn.flash_attn_varlen_func (FA2 mma.sync kernels) called from
+// wan/modules/attention.py:113-127 for self-attention (model.py:146-151) and cross-attention (:176).
 //
+// This file holds four kernels that share one CTA shape (one head x 256 query rows = two 128-row Q tiles, K/V streamed
+// by TMA through a shared-memory ring, tcgen05.mma issued by one warp per Q tile, S / P / O in TMEM):
+//
+//   attention_fwd_k128_kernel    THE DEFAULT.  128-key steps, one 128-column score buffer per tile (S_0 | S_1 | O_0 | O_1
+//                                = 512 TMEM columns), M128 N128 MMAs, fixed-reference softmax (STALE = true: no row max
+//                                in the steady state, overflow-guarded exact redo).  1.28-1.42 PFLOP/s alone,
+//                                1.07-1.19 PFLOP/s inside the power-capped 14B step.  STALE = false: classic online softmax.
+//   attention_fwd_kernel         64-key steps with double-buffered scores (MV_ATTN_KSTEP=64): the first design; its N64
+//                                score MMAs are shared-memory-bandwidth bound (192 B/clk), 1.19-1.24 PFLOP/s alone.
+//   attention_fwd_k128x2_kernel  MV_ATTN_SPLIT=1: two threads per query row, 16 softmax warps.  Measured, not faster.
+//   attention_fwd_k128p_kernel   MV_ATTN_SPLIT=2: two threads per row, the warpgroups alternate between the tiles.  Same.
+//
+// What the measurements behind these variants showed (profiles/README.md, "attention" section): per Q tile the chain
+// softmax(j) -> P.V(j) -> Q.K(j+1)^T -> softmax(j+1) is serial, the two tiles run in (self-organised, imperfect)
+// antiphase, and the per-tile softmax time is the lever: 128 exponentials per thread cost 1233 clk for a lone warp
+// (MUFU-bound would be 1024), the row max another ~350 clk — dropping the row max is worth +13 % alone and +6.6 % in
+// the step, whereas packing two warps per sub-partition on a tile (the split kernels) or emulating part of the
+// exponentials on the FMA pipe did not pay with 128-key steps.  Inside the 14B step the kernel runs under the 1000 W
+// power cap (SM clock 1.5-1.7 GHz), so fewer instructions per score also means a higher clock.
+//
+// ---- 64-key kernel ----------------------------------------------------------------------------------------------
 // One CTA = one head x 256 query rows = two 128-row Q tiles (w = 0, 1).  Keys are consumed in steps of 64.
 //   warp 0       TMA producer: Q (once), then K_0, K_1, V_0, K_2, V_1, ... through an 8 x 16 KB ring
-//   warp 1       MMA issuer (one thread):  S_w[b] = Q_w K_j^T  (SS, M128 N64 K16 x 8)
-//                                          O_w   += P_w[b] V_j (A = P from TMEM, B = V MN-major smem, N128 K16 x 4)
+//   warps 1, 2   MMA issuers (one per Q tile):  S_w[b] = Q_w K_j^T  (SS, M128 N64 K16 x 8)
+//                                               O_w   += P_w[b] V_j (A = P from TMEM, B = V MN-major smem, N128 K16 x 4)
 //   warps 4-7    softmax warpgroup for Q tile 0: one thread per query row
 //   warps 8-11   same for Q tile 1
 // TMEM (512 columns): S_0[0] S_0[1] S_1[0] S_1[1] (4 x 64 fp32 columns) | O_0 | O_1 (2 x 128).  P (bf16, 32 columns)
@@ -14,9 +37,6 @@
 // Online softmax in fp32 with exp2; the O accumulator is rescaled lazily (only when a row max grew by more than
 // 2^8, FA4-style) by the softmax warpgroup itself after waiting for the previous P.V; final 1/l scaling and bf16
 // store by the same threads.
-//
-// Replaces flash_attn.flash_attn_varlen_func (FA2 mma.sync kernels) called from
-// wan/modules/attention.py:113-127 for self-attention (model.py:146-151) and cross-attention (:176).
 #include <math.h>
 #include <stdlib.h>
 
