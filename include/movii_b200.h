@@ -200,11 +200,10 @@ int mv_attention_fwd_trace(const void* q, int64_t ldq, const void* k, int64_t ld
                            int trace_steps, mv_stream_t stream);
 
 /* Diagnostics only: overrides the attention kernel variant chosen from the environment (MV_ATTN_KSTEP / _EMU / _STALE /
- * _PINGPONG / _SPLIT) for A/B timing inside one process; a negative argument keeps the current value.  kstep 64 | 128,
- * emu 0..2 (fraction of exponentials on the FMA pipe: none, 1/4, 1/2), split 1 | 2 = two threads per query row
- * (16 softmax warps | paired warpgroups), skew = one-time start offset of the second Q tile (clocks).
- * tools/ab_step.py. */
-int mv_attention_config(int kstep, int emu, int stale, int pingpong, int split, int skew);
+ * _PINGPONG / _SKEW) for A/B timing inside one process; a negative argument keeps the current value.  kstep 64 | 128,
+ * emu 0..2 (fraction of exponentials on the FMA pipe: none, 1/4, 1/2), stale 1 = fixed-reference softmax (128-key
+ * kernel), skew = one-time start offset of the second Q tile (clocks).  tools/ab_step.py. */
+int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew);
 
 /* ---- umT5 text encoder (caller side of the hot path) --------------------------- */
 

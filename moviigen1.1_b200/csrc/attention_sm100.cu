@@ -2,7 +2,7 @@
 // Replaces flash_attn.flash_attn_varlen_func (FA2 mma.sync kernels) called from
 // wan/modules/attention.py:113-127 for self-attention (model.py:146-151) and cross-attention (:176).
 //
-// This file holds four kernels that share one CTA shape (one head x 256 query rows = two 128-row Q tiles, K/V streamed
+// This file holds two kernels that share one CTA shape (one head x 256 query rows = two 128-row Q tiles, K/V streamed
 // by TMA through a shared-memory ring, tcgen05.mma issued by one warp per Q tile, S / P / O in TMEM):
 //
 //   attention_fwd_k128_kernel    THE DEFAULT.  128-key steps, one 128-column score buffer per tile (S_0 | S_1 | O_0 | O_1
@@ -11,14 +11,15 @@
 //                                1.07-1.19 PFLOP/s inside the power-capped 14B step.  STALE = false: classic online softmax.
 //   attention_fwd_kernel         64-key steps with double-buffered scores (MV_ATTN_KSTEP=64): the first design; its N64
 //                                score MMAs are shared-memory-bandwidth bound (192 B/clk), 1.19-1.24 PFLOP/s alone.
-//   attention_fwd_k128x2_kernel  MV_ATTN_SPLIT=1: two threads per query row, 16 softmax warps.  Measured, not faster.
-//   attention_fwd_k128p_kernel   MV_ATTN_SPLIT=2: two threads per row, the warpgroups alternate between the tiles.  Same.
+// Two more were written, validated (all GPU tests green) and measured this round, then removed because they did not
+// pay (source: git commit cf8d306; numbers: profiles/README.md items 7-9): two threads per query row with 16 softmax
+// warps, and two threads per row with the two warpgroups alternating between the tiles.
 //
 // What the measurements behind these variants showed (profiles/README.md, "attention" section): per Q tile the chain
 // softmax(j) -> P.V(j) -> Q.K(j+1)^T -> softmax(j+1) is serial, the two tiles run in (self-organised, imperfect)
 // antiphase, and the per-tile softmax time is the lever: 128 exponentials per thread cost 1233 clk for a lone warp
 // (MUFU-bound would be 1024), the row max another ~350 clk — dropping the row max is worth +13 % alone and +6.6 % in
-// the step, whereas packing two warps per sub-partition on a tile (the split kernels) or emulating part of the
+// the step, whereas packing two warps per sub-partition on a tile (the removed row-split kernels) or emulating part of the
 // exponentials on the FMA pipe did not pay with 128-key steps.  Inside the 14B step the kernel runs under the 1000 W
 // power cap (SM clock 1.5-1.7 GHz), so fewer instructions per score also means a higher clock.
 //
@@ -54,8 +55,6 @@ constexpr int kDefaultEmu64 = 1;    // 64-key kernel: 1/4 of the exponentials on
 constexpr int kDefaultEmu128 = 0;   // 128-key kernel: MUFU only (the emulation lengthens the per-tile critical path: -18 %)
 constexpr int kDefaultStale = 1;     // 128-key kernel: fixed-reference softmax (no per-step row max): 1371 vs 1209 TF/s alone,
                                      // 1137 vs 1067 TF/s inside the power-capped 720P step; MV_ATTN_STALE=0: classic online softmax
-constexpr int kDefaultSplit = 0;     // MV_ATTN_SPLIT=1: two threads per query row, 16 softmax warps (attention_fwd_k128x2_kernel);
-                                     // 2: two threads per row, the two warpgroups alternate between the tiles (.._k128p_kernel)
 constexpr int kDefaultKStep = 128;   // 128-key-step kernel below (in the 14B 720P step: 1019 vs 946 TF/s); MV_ATTN_KSTEP=64: the kernel above
 constexpr int kDefaultSkewNs = 0;
 constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
@@ -874,724 +873,16 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 }
 
 
-// ================================================================================================================
-// Row-split variant of the 128-key-step kernel (MV_ATTN_SPLIT=1): the same TMEM / ring / MMA choreography, but TWO
-// threads per query row — 16 softmax warps: tile w = warps 4+8w .. 11+8w, the first four take keys 0..63 of the step,
-// the other four keys 64..127 (warp % 4 = TMEM lane quadrant for both).  Why: with the two Q tiles in antiphase only
-// ONE softmax warp per SM sub-partition is active at a time, and a lone in-order warp cannot keep the 4-lane MUFU pipe
-// full (tools/probe/softmax_pipe_probe.cu: 1233 clk per 128 exponentials alone vs 1043 clk with two warps sharing the
-// sub-partition); the row max, TMEM load, bf16 pack and P store of the step are halved per thread as well.  The two
-// half-row threads exchange their partial row max through shared memory (one 64-thread named barrier per step, which
-// also orders "partner has read its scores" before P overwrites them); partial row sums are combined once, in the
-// epilogue; each thread rescales / writes its own 64 columns of O.
-// ================================================================================================================
-constexpr int kAttnThreadsX2 = 640;
-constexpr uint32_t kXchBytes = 2 * 2 * 2 * kBQ * 4;   // [parity][tile][half][row] fp32
-constexpr uint32_t kAttnSmemX2 = kAttnSmem2 + kXchBytes;
-
-template <int EMU, bool TRACE, bool FIXREF>
-__global__ void __launch_bounds__(kAttnThreadsX2, 1)
-attention_fwd_k128x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                            const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                        // 2 tiles
-  uint8_t* sKV = smem + 2 * kQTileBytes;     // ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* kv_full = bars + 1;               // kKVStages2
-  uint64_t* kv_empty = kv_full + kKVStages2;  // kKVStages2
-  uint64_t* s_full = kv_empty + kKVStages2;   // [w] -> 2
-  uint64_t* p_full = s_full + 2;              // [w] -> 2
-  uint64_t* o_done = p_full + 2;              // [w] -> 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-  float* xch = reinterpret_cast<float*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 512);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * kBQ);
-  const int n_kv = (p.Lk + kBKV2 - 1) / kBKV2;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kKVStages2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);  // released by both tiles' issuing warps
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);  // one arrive per softmax warp of the tile
-      mbar_init(&o_done[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    // register budget of the CTA pool: 640 x 96 at launch; the four producer warps give back 4 x 32 x 64 = 8192, which
-    // is exactly what the sixteen softmax warps need to go from 96 to 112 (setmaxnreg only moves registers inside the
-    // CTA's own allocation: asking for more than was released blocks for ever)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    if (warp == 0) {
-      // ------------------------------ TMA producer: Q, K_0, then V_j, K_{j+1} ------------------------------
-      if (elect_one()) {
-        mbar_expect_tx(q_full, 2 * kQTileBytes);
-#pragma unroll
-        for (int w = 0; w < 2; ++w)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      auto load_tile = [&](const CUtensorMap* tm, int j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&kv_full[stage], kKVTileBytes2);
-          tma_load_3d(sKV + stage * kKVTileBytes2, tm, &kv_full[stage], 0, head, j * kBKV2);
-          tma_load_3d(sKV + stage * kKVTileBytes2 + kKVHalfBytes2, tm, &kv_full[stage], 64, head, j * kBKV2);
-        }
-        __syncwarp();
-        if (++stage == kKVStages2) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      load_tile(&tmK, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        load_tile(&tmV, j);
-        if (j + 1 < n_kv) load_tile(&tmK, j + 1);
-      }
-    } else if (warp == 1 || warp == 2) {
-      // ------------------------------ MMA issuers: one warp per Q tile (as in the kernel above) -------------
-      // Descriptors as (low, high) words: this warp runs on 32 registers (setmaxnreg.dec) so that the 16 softmax
-      // warps can have 112 each.
-      constexpr uint32_t idesc_qk = make_idesc_bf16(kBQ, kBKV2, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
-      const int w = warp - 1;
-      const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ) + w * kQTileBytes);
-      const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV));
-      const uint64_t vdesc = make_desc_mnmajor_sw128(smem_u32(sKV), kKVHalfBytes2);
-      const uint32_t q_lo = static_cast<uint32_t>(qdesc), k_lo0 = static_cast<uint32_t>(kdesc), v_lo0 = static_cast<uint32_t>(vdesc);
-      const uint32_t qk_hi = static_cast<uint32_t>(kdesc >> 32), v_hi = static_cast<uint32_t>(vdesc >> 32);
-      const uint32_t tS = tmem_base + w * 128;
-      const uint32_t tO = tmem_base + 256 + w * 128;
-      auto issue_qk = [&](int st) {
-        const uint32_t k_lo = k_lo0 + st * (kKVTileBytes2 >> 4);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint32_t qo = ((k >> 2) * kQHalfBytes + (k & 3) * 32) >> 4;
-          const uint32_t ko = ((k >> 2) * kKVHalfBytes2 + (k & 3) * 32) >> 4;
-          umma_ss_lh(tS, q_lo + qo, qk_hi, k_lo + ko, qk_hi, idesc_qk, k != 0 ? 1u : 0u);
-        }
-      };
-      auto issue_pv = [&](int st, uint32_t acc) {
-        const uint32_t v_lo = v_lo0 + st * (kKVTileBytes2 >> 4);
-#pragma unroll
-        for (int k = 0; k < kBKV2 / 16; ++k) umma_ts_lh(tO, tS + k * 8, v_lo + ((k * 2048) >> 4), v_hi, idesc_pv, (acc | k) != 0 ? 1u : 0u);
-      };
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++stage == kKVStages2) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_qk(stage);
-        umma_commit(&s_full[w]);
-        umma_commit(&kv_empty[stage]);
-      }
-      __syncwarp();
-      advance();
-      for (int j = 0; j < n_kv; ++j) {
-        const int vstage = stage;
-        const uint32_t vphase = phase;
-        advance();
-        const bool more = (j + 1 < n_kv);
-        const int kstage = stage;
-        const uint32_t kphase = phase;
-        if (more) advance();
-        mbar_wait(&kv_full[vstage], vphase);
-        if (more) mbar_wait(&kv_full[kstage], kphase);
-        mbar_wait(&p_full[w], j & 1);
-        tc_fence_after();
-        if constexpr (TRACE) {
-          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
-            p.trace[(w * p.trace_steps + j) * 8 + 5] = clock64();
-        }
-        if (elect_one()) {
-          issue_pv(vstage, j > 0 ? 1u : 0u);
-          umma_commit(&o_done[w]);
-          umma_commit(&kv_empty[vstage]);
-          if (more) {
-            issue_qk(kstage);   // in issue order behind P.V(j): overwrites the S/P buffer only after P was read
-            umma_commit(&s_full[w]);
-            umma_commit(&kv_empty[kstage]);
-          }
-        }
-        __syncwarp();
-        if constexpr (TRACE) {
-          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
-            p.trace[(w * p.trace_steps + j) * 8 + 6] = clock64();
-        }
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    // ------------------------------ softmax: 2 tiles x 2 key halves x 4 lane quadrants ------------------------
-    const int sw = warp - 4;
-    const int wg = sw >> 3;          // Q tile
-    const int hf = (sw >> 2) & 1;    // key half of every step (and column half of O)
-    const int quad = warp & 3;       // TMEM lane quadrant
-    const int rloc = quad * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + wg * 128 + hf * 64;        // this thread's 64 scores
-    const uint32_t tP = tmem_base + lane_base + wg * 128 + hf * 32;        // its 32 packed-bf16 columns of P
-    const uint32_t tO = tmem_base + lane_base + 256 + wg * 128 + hf * 64;  // its 64 columns of O
-    const float sl2 = p.scale_log2;
-    const int bar_id = 1 + wg * 4 + quad;   // named barrier of the two warps that share these 32 rows
-    float* xmine = xch + (wg * 2 + hf) * kBQ + rloc;
-    float* xpeer = xch + (wg * 2 + (hf ^ 1)) * kBQ + rloc;
-    float m_run = -INFINITY;   // classic: running row max of raw scores (identical in both threads of a row)
-    float ref2 = 0.f;          // fixed-reference: P = 2^(s * scale_log2 - ref2) (identical in both threads of a row)
-    float l_run = 0.f;         // row sum over THIS thread's keys
-    auto rescale_o = [&](float alpha) {   // this thread's 64 columns of O
-      l_run *= alpha;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld_x32(tO + c * 32, o);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_x32(tO + c * 32, o);
-      }
-    };
-
-    for (int j = 0; j < n_kv; ++j) {
-      const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && hf == 0 && lane == 0 && j < p.trace_steps;
-      unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
-      if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);   // completes before s_full(j); every phase observed in order
-      mbar_wait(&s_full[wg], j & 1);
-      tc_fence_after();
-      if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
-      uint32_t s[2][32];
-      const int valid = p.Lk - j * kBKV2 - hf * 64;
-      auto load_scores = [&]() {
-        tmem_ld_x32(tS, s[0]);
-        tmem_ld_x32(tS + 32, s[1]);
-        tc_wait_ld();
-        if (valid < 64) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-        }
-      };
-      auto local_max = [&]() {
-        float mx[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          mx[c] = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 16; i += 2)
-            mx[c] = fmax3(mx[c], __uint_as_float(s[c >> 1][(c & 1) * 16 + i]), __uint_as_float(s[c >> 1][(c & 1) * 16 + i + 1]));
-        }
-        return fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], -INFINITY);
-      };
-      // pair exchange through shared memory: publish `mine`, meet the partner (64-thread named barrier), read its value.
-      // Slots are double-buffered by `slot` parity: a slot is rewritten two exchanges later, i.e. after a barrier that the
-      // partner only passes once it has read the previous value.
-      auto exchange = [&](float mine, int slot) {
-        xmine[slot * (4 * kBQ)] = mine;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        return xpeer[slot * (4 * kBQ)];
-      };
-      float2 sum2;
-      uint32_t pk[32];
-      auto exp_pass = [&](float neg_ref) {   // pk = bf16(2^(s * scale_log2 + neg_ref)), sum2 = their fp32 sums
-        const float2 sc2 = make_float2(sl2, sl2);
-        const float2 nm2 = make_float2(neg_ref, neg_ref);
-        sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-            const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-            float2 e01, e23;
-            e01.x = fast_exp2(x01.x);
-            e01.y = (EMU >= 2) ? exp2_emu(FIXREF ? fminf(x01.y, 126.f) : x01.y) : fast_exp2(x01.y);
-            e23.x = fast_exp2(x23.x);
-            e23.y = (EMU >= 1) ? exp2_emu(FIXREF ? fminf(x23.y, 126.f) : x23.y) : fast_exp2(x23.y);
-            sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
-            pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
-            pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
-          }
-        }
-      };
-      load_scores();
-      if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
-      if constexpr (FIXREF) {
-        // ---- fixed reference (see the 128-key kernel above): no row max in the steady state.  Per step the pair meets
-        // once, right before the P stores, to (a) agree whether either half overflowed (then both redo the step with
-        // the exact row max) and (b) order "partner's scores are in its registers" before P overwrites them.
-        if (j == 0) ref2 = fmaxf(local_max(), exchange(local_max(), 0)) * sl2;   // exact row max of the first step
-        if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
-        exp_pass(-ref2);
-        const float ovf = __any_sync(0xffffffffu, !(sum2.x + sum2.y <= 1.8446744073709552e19f)) ? 1.f : 0.f;   // 2^64
-        const float peer_ovf = exchange(ovf, (j + 1) & 1);   // (step 0 used slot 0 for the row max)
-        if (ovf + peer_ovf != 0.f) {   // same for all 64 threads of the pair (the flags are warp-uniform)
-          load_scores();               // nothing has been stored yet: the scores are still in TMEM
-          const float m_loc = local_max();
-          const float m_row = fmaxf(m_loc, exchange(m_loc, j & 1));   // (also: both halves have re-read their scores)
-          // the next regular exchange re-uses this slot: make sure the partner has read it before moving on
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-          const float up = fmaxf(m_row * sl2 - ref2, 0.f);
-          rescale_o(fast_exp2(-up));   // P.V(j-1) has landed (o_done probed above)
-          ref2 += up;
-          exp_pass(-ref2);             // exact reference: cannot overflow
-        }
-      } else {
-        const float m_loc = local_max();
-        // exchange with the thread that holds the other 64 keys of this row.  The barrier also guarantees that the
-        // partner's scores are in its registers before this thread's P overwrites them (P of keys 64..127 lands on the
-        // columns that held the scores of keys 32..63).
-        const float m_new = fmax3(m_run, m_loc, exchange(m_loc, j & 1));
-        if (j == 0) {
-          m_run = m_new;
-        } else {
-          const bool need = (m_new - m_run) * sl2 > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {   // same rows, same values: both warps of the pair take the same branch
-            rescale_o(fast_exp2((m_run - m_new) * sl2));
-            m_run = m_new;
-          }
-        }
-        if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
-        exp_pass(-m_run * sl2);
-      }
-      l_run += sum2.x + sum2.y;
-      if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
-      tmem_st_x32(tP, pk);
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[wg]);
-      if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
-    }
-
-    // ------------------------------ final epilogue ----------------------------
-    mbar_wait(&o_done[wg], (n_kv - 1) & 1);
-    tc_fence_after();
-    {   // total row sum = this thread's keys + the partner's, through the slot the last step did NOT use
-      const int slot = FIXREF ? ((n_kv + 1) & 1) : (n_kv & 1);
-      xmine[slot * (4 * kBQ)] = l_run;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      l_run += xpeer[slot * (4 * kBQ)];
-    }
-    const float inv_l = 1.0f / l_run;
-    const int row = q0 + wg * kBQ + rloc;
-    __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * kD + hf * 64;
-    if (p.n_dst > 0 && row < p.Lq) {
-      const int dst = row / p.rows_per_rank;
-      const int rl = row - dst * p.rows_per_rank;
-      orow = p.o_dst[dst] + (static_cast<int64_t>(p.src_rank) * p.rows_per_rank + rl) * p.ldo + head * kD + hf * 64;
-    }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_x32(tO + c * 32, o);
-      tc_wait_ld();
-      if (row < p.Lq) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          dst[i] = w;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-
-// ================================================================================================================
-// Paired-warpgroup variant (MV_ATTN_SPLIT=2): same CTA shape as the 128-key kernel (384 threads, helpers on 64
-// registers), but the two softmax warpgroups do not own a Q tile each: BOTH work on the same tile-step, warps 4..7 on
-// keys 0..63 and warps 8..11 on keys 64..127 of every row (two threads per row), and they alternate between the two
-// Q tiles: (step 0, tile 0), (step 0, tile 1), (step 1, tile 0), ...  Two warps per SM sub-partition are then always in
-// the exponential pass together, which is what it takes to keep the 4-lane MUFU pipe full (tools/probe: 1043 clk per
-// 128 x 32 exponentials with two warps vs 1233 alone), while the tensor work of one tile (P.V, next Q.K^T) runs under
-// the softmax of the other.  Fixed-reference softmax (see above); the pair meets once per tile-step, before the P
-// stores, to agree on overflow and to order "partner's scores are in registers" before P overwrites them.
-// ================================================================================================================
-constexpr uint32_t kXchBytesP = 2 * 2 * kBQ * 4;   // [slot][half][row] fp32
-constexpr uint32_t kAttnSmemP = kAttnSmem2 + kXchBytesP;
-
-template <int EMU, bool TRACE>
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attention_fwd_k128p_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                           const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr bool PP = false;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                        // 2 tiles
-  uint8_t* sKV = smem + 2 * kQTileBytes;     // ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* kv_full = bars + 1;               // kKVStages2
-  uint64_t* kv_empty = kv_full + kKVStages2;  // kKVStages2
-  uint64_t* s_full = kv_empty + kKVStages2;   // [w] -> 2
-  uint64_t* p_full = s_full + 2;              // [w] -> 2
-  uint64_t* o_done = p_full + 2;              // [w] -> 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-  float* xch = reinterpret_cast<float*>(smem + 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 512);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * kBQ);
-  const int n_kv = (p.Lk + kBKV2 - 1) / kBKV2;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kKVStages2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);  // released by both tiles' issuing warps
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);  // one arrive per softmax warp (all eight work on every tile-step)
-      mbar_init(&o_done[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == 0) {
-      // ------------------------------ TMA producer: Q, K_0, then V_j, K_{j+1} ------------------------------
-      if (elect_one()) {
-        mbar_expect_tx(q_full, 2 * kQTileBytes);
-#pragma unroll
-        for (int w = 0; w < 2; ++w)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_3d(sQ + w * kQTileBytes + h * kQHalfBytes, &tmQ, q_full, h * 64, head, q0 + w * kBQ);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      auto load_tile = [&](const CUtensorMap* tm, int j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&kv_full[stage], kKVTileBytes2);
-          tma_load_3d(sKV + stage * kKVTileBytes2, tm, &kv_full[stage], 0, head, j * kBKV2);
-          tma_load_3d(sKV + stage * kKVTileBytes2 + kKVHalfBytes2, tm, &kv_full[stage], 64, head, j * kBKV2);
-        }
-        __syncwarp();
-        if (++stage == kKVStages2) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      load_tile(&tmK, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        load_tile(&tmV, j);
-        if (j + 1 < n_kv) load_tile(&tmK, j + 1);
-      }
-    } else if (warp == 1 || warp == 2) {
-      // ------------------------------ MMA issuers: one warp per Q tile -------------------------------
-      constexpr uint32_t idesc_qk = make_idesc_bf16(kBQ, kBKV2, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kBQ, kD, 0, 1);
-      const int w = warp - 1;
-      const uint64_t qdesc0 = make_desc_kmajor_sw128(smem_u32(sQ)) + ((w * kQTileBytes) >> 4);
-      const uint64_t kdesc0 = make_desc_kmajor_sw128(smem_u32(sKV));
-      const uint64_t vdesc0 = make_desc_mnmajor_sw128(smem_u32(sKV), kKVHalfBytes2);
-      const uint32_t tS = tmem_base + w * 128;
-      const uint32_t tO = tmem_base + 256 + w * 128;
-      // S_w = Q_w K^T : 8 x (M128 N128 K16)
-      auto issue_qk = [&](int st) {
-        const uint64_t kd = kdesc0 + ((st * kKVTileBytes2) >> 4);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint32_t qo = ((k >> 2) * kQHalfBytes + (k & 3) * 32) >> 4;
-          const uint32_t ko = ((k >> 2) * kKVHalfBytes2 + (k & 3) * 32) >> 4;
-          umma_ss(tS, qdesc0 + qo, kd + ko, idesc_qk, k != 0 ? 1u : 0u);
-        }
-      };
-      // O_w (+)= P_w V : 8 x (M128 N128 K16), A = P from TMEM (64 columns of packed bf16 pairs).
-      // (Handing P over in two 64-key halves so that the first half of P.V overlaps the second half's exponentials
-      // was measured: the mid-step tcgen05.wait::st + barrier arrive cost 14 % (1358 -> 1172 TF/s) — not done.)
-      auto issue_pv = [&](int st, uint32_t acc) {
-        const uint64_t vd = vdesc0 + ((st * kKVTileBytes2) >> 4);
-#pragma unroll
-        for (int k = 0; k < kBKV2 / 16; ++k) umma_ts(tO, tS + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
-      };
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++stage == kKVStages2) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_qk(stage);
-        umma_commit(&s_full[w]);
-        umma_commit(&kv_empty[stage]);
-      }
-      __syncwarp();
-      advance();
-      for (int j = 0; j < n_kv; ++j) {
-        const int vstage = stage;
-        const uint32_t vphase = phase;
-        advance();
-        const bool more = (j + 1 < n_kv);
-        const int kstage = stage;
-        const uint32_t kphase = phase;
-        if (more) advance();
-        mbar_wait(&kv_full[vstage], vphase);
-        if (more) mbar_wait(&kv_full[kstage], kphase);
-        mbar_wait(&p_full[w], j & 1);
-        tc_fence_after();
-        if constexpr (TRACE) {
-          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
-            p.trace[(w * p.trace_steps + j) * 8 + 5] = clock64();
-        }
-        if (elect_one()) {
-          issue_pv(vstage, j > 0 ? 1u : 0u);
-          umma_commit(&o_done[w]);
-          umma_commit(&kv_empty[vstage]);
-          if (more) {
-            // right behind P.V(j): this thread's MMAs execute in issue order, so the scores of step j+1 overwrite
-            // the S/P buffer only after P.V(j) has read P from it
-            issue_qk(kstage);
-            umma_commit(&s_full[w]);
-            umma_commit(&kv_empty[kstage]);
-          }
-        }
-        __syncwarp();
-        if constexpr (TRACE) {
-          if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
-            p.trace[(w * p.trace_steps + j) * 8 + 6] = clock64();
-        }
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    // ------------------------------ softmax: 2 key halves x 4 lane quadrants, both tiles in turn --------------
-    const int hf = (warp - 4) >> 2;   // key half of every step (and column half of O)
-    const int quad = warp & 3;        // TMEM lane quadrant
-    const int rloc = quad * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const float sl2 = p.scale_log2;
-    const int bar_id = 1 + quad;      // named barrier of the two warps that share these 32 rows
-    float* xmine = xch + hf * kBQ + rloc;
-    float* xpeer = xch + (hf ^ 1) * kBQ + rloc;
-    int xs = 0;                       // exchange counter: slots alternate, so a slot is only rewritten after a barrier
-                                      // that the partner passes once it has read the previous value
-    auto exchange = [&](float mine) {
-      const int off = (xs & 1) * (2 * kBQ);
-      ++xs;
-      xmine[off] = mine;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      return xpeer[off];
-    };
-    float ref2[2] = {0.f, 0.f};    // per tile: P = 2^(s * scale_log2 - ref2) (identical in both threads of a row)
-    float l_run[2] = {0.f, 0.f};   // per tile: row sum over THIS thread's keys
-
-    for (int j = 0; j < n_kv; ++j) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const uint32_t tS = tmem_base + lane_base + w * 128 + hf * 64;        // this thread's 64 scores
-        const uint32_t tP = tmem_base + lane_base + w * 128 + hf * 32;        // its 32 packed-bf16 columns of P
-        const uint32_t tO = tmem_base + lane_base + 256 + w * 128 + hf * 64;  // its 64 columns of O
-        const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && hf == 0 && lane == 0 && j < p.trace_steps;
-        unsigned long long* trow = TRACE ? p.trace + (w * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
-        if (j > 0) mbar_wait(&o_done[w], (j - 1) & 1);   // completes before s_full(j); every phase observed in order
-        mbar_wait(&s_full[w], j & 1);
-        tc_fence_after();
-        if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
-        uint32_t s[2][32];
-        const int valid = p.Lk - j * kBKV2 - hf * 64;
-        auto load_scores = [&]() {
-          tmem_ld_x32(tS, s[0]);
-          tmem_ld_x32(tS + 32, s[1]);
-          tc_wait_ld();
-          if (valid < 64) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-          }
-        };
-        auto local_max = [&]() {
-          float mx[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            mx[c] = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 16; i += 2)
-              mx[c] = fmax3(mx[c], __uint_as_float(s[c >> 1][(c & 1) * 16 + i]), __uint_as_float(s[c >> 1][(c & 1) * 16 + i + 1]));
-          }
-          return fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], -INFINITY);
-        };
-        float2 sum2;
-        uint32_t pk[32];
-        auto exp_pass = [&](float neg_ref) {   // pk = bf16(2^(s * scale_log2 + neg_ref)), sum2 = their fp32 sums
-          const float2 sc2 = make_float2(sl2, sl2);
-          const float2 nm2 = make_float2(neg_ref, neg_ref);
-          sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-              const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-              float2 e01, e23;
-              e01.x = fast_exp2(x01.x);
-              e01.y = (EMU >= 2) ? exp2_emu(fminf(x01.y, 126.f)) : fast_exp2(x01.y);
-              e23.x = fast_exp2(x23.x);
-              e23.y = (EMU >= 1) ? exp2_emu(fminf(x23.y, 126.f)) : fast_exp2(x23.y);
-              sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
-              pk[c * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
-              pk[c * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
-            }
-          }
-        };
-        load_scores();
-        if constexpr (TRACE) { if (tr) trow[1] = clock64(); }
-        if (j == 0) {   // the first step fixes the reference at the exact row max
-          const float m_loc = local_max();
-          ref2[w] = fmaxf(m_loc, exchange(m_loc)) * sl2;
-        }
-        if constexpr (TRACE) { if (tr) trow[2] = clock64(); }
-        exp_pass(-ref2[w]);
-        const float ovf = __any_sync(0xffffffffu, !(sum2.x + sum2.y <= 1.8446744073709552e19f)) ? 1.f : 0.f;   // 2^64
-        const float peer_ovf = exchange(ovf);
-        if (ovf + peer_ovf != 0.f) {   // same for all 64 threads of the pair (the flags are warp-uniform)
-          load_scores();               // nothing has been stored yet: the scores are still in TMEM
-          const float m_loc = local_max();
-          const float m_row = fmaxf(m_loc, exchange(m_loc));   // (also: both halves have re-read their scores)
-          const float up = fmaxf(m_row * sl2 - ref2[w], 0.f);
-          const float alpha = fast_exp2(-up);
-          l_run[w] *= alpha;           // P.V(j-1) of this tile has landed (o_done probed above)
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_x32(tO + c * 32, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x32(tO + c * 32, o);
-          }
-          ref2[w] += up;
-          exp_pass(-ref2[w]);          // exact reference: cannot overflow
-        }
-        l_run[w] += sum2.x + sum2.y;
-        if constexpr (TRACE) { if (tr) trow[3] = clock64(); }
-        tmem_st_x32(tP, pk);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[w]);
-        if constexpr (TRACE) { if (tr) trow[4] = clock64(); }
-      }
-    }
-
-    // ------------------------------ final epilogue ----------------------------
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const uint32_t tO = tmem_base + lane_base + 256 + w * 128 + hf * 64;
-      mbar_wait(&o_done[w], (n_kv - 1) & 1);
-      tc_fence_after();
-      const float l_tot = l_run[w] + exchange(l_run[w]);   // this thread's keys + the partner's
-      const float inv_l = 1.0f / l_tot;
-      const int row = q0 + w * kBQ + rloc;
-      __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * kD + hf * 64;
-      if (p.n_dst > 0 && row < p.Lq) {
-        const int dst = row / p.rows_per_rank;
-        const int rl = row - dst * p.rows_per_rank;
-        orow = p.o_dst[dst] + (static_cast<int64_t>(p.src_rank) * p.rows_per_rank + rl) * p.ldo + head * kD + hf * 64;
-      }
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld_x32(tO + c * 32, o);
-        tc_wait_ld();
-        if (row < p.Lq) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 v4;
-            v4.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-            v4.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-            v4.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-            v4.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-            dst[i] = v4;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 }  // namespace mv
 
 // Kernel-variant knobs: environment defaults (read once), overridable at run time through mv_attention_config
 // (A/B measurements inside one process; the product path never calls it).
 namespace {
 struct AttnKnobs {
-  int kstep, emu, stale, pingpong, order, skew, split;
+  int kstep, emu, stale, pingpong, order, skew;
   bool init;
 };
-AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, 0, false};
+AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, false};
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
@@ -1607,15 +898,13 @@ AttnKnobs& attn_knobs() {
     g_knobs.pingpong = env_int("MV_ATTN_PINGPONG", mv::kDefaultPingPong);
     g_knobs.order = env_int("MV_ATTN_ORDER", 0) == 1 ? 1 : 0;   // default 0: same speed since each tile has its own issuer
     g_knobs.skew = env_int("MV_ATTN_SKEW", mv::kDefaultSkewNs);
-    g_knobs.split = env_int("MV_ATTN_SPLIT", mv::kDefaultSplit);
-    if (g_knobs.split < 0 || g_knobs.split > 2) g_knobs.split = mv::kDefaultSplit;
     g_knobs.init = true;
   }
   return g_knobs;
 }
 }  // namespace
 
-extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int split, int skew) {
+extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew) {
   AttnKnobs& kn = attn_knobs();
   if ((kstep >= 0 && kstep != 64 && kstep != 128) || emu > 2) {
     mv::set_error("mv_attention_config: kstep must be 64 or 128, emu 0..2 (negative = keep)");
@@ -1625,7 +914,6 @@ extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, 
   if (emu >= 0) kn.emu = emu;
   if (stale >= 0) kn.stale = stale;
   if (pingpong >= 0) kn.pingpong = pingpong;
-  if (split >= 0) kn.split = split <= 2 ? split : 0;
   if (skew >= 0) kn.skew = skew;
   return MV_OK;
 }
@@ -1655,7 +943,8 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     return make_tmap_bf16(tm, base, 3, dims, str, box, true);
   };
   const AttnKnobs& kn = attn_knobs();
-  const int kstep = kn.kstep;   // keys per softmax step: 64 (double-buffered scores) or 128
+  const int kstep = trace != nullptr ? 128 : kn.kstep;   // keys per softmax step: 64 (double-buffered scores) or 128
+                                                         // (the trace entry point exists for the 128-key kernel only)
   if ((rc = mk(&tmQ, q, ldq, Lq, kBQ)) != MV_OK) return rc;
   if ((rc = mk(&tmK, k, ldk, Lk, kstep)) != MV_OK) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, kstep)) != MV_OK) return rc;
@@ -1715,48 +1004,11 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem2)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128x2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemX2)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128p_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemP)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128p_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemP)));
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128p_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kAttnSmemP)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((kstep == 128 || p.trace != nullptr) && kn.split == 2 && softmax_scale > 0.f) {
-    if (p.trace != nullptr) attention_fwd_k128p_kernel<0, true><<<grid, kAttnThreads, kAttnSmemP, st>>>(tmQ, tmK, tmV, p);
-    else if (emu >= 1) attention_fwd_k128p_kernel<1, false><<<grid, kAttnThreads, kAttnSmemP, st>>>(tmQ, tmK, tmV, p);
-    else attention_fwd_k128p_kernel<0, false><<<grid, kAttnThreads, kAttnSmemP, st>>>(tmQ, tmK, tmV, p);
-    MV_CHECK_LAUNCH("attention_fwd_k128p_kernel");
-    return MV_OK;
-  }
-  if ((kstep == 128 || p.trace != nullptr) && kn.split) {
-    const bool fix = kn.stale != 0 && softmax_scale > 0.f;
-    const dim3 blk(kAttnThreadsX2);
-    if (p.trace != nullptr && fix) attention_fwd_k128x2_kernel<0, true, true><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else if (p.trace != nullptr) attention_fwd_k128x2_kernel<0, true, false><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else if (fix && emu >= 1) attention_fwd_k128x2_kernel<1, false, true><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else if (fix) attention_fwd_k128x2_kernel<0, false, true><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else if (emu >= 1) attention_fwd_k128x2_kernel<1, false, false><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    else attention_fwd_k128x2_kernel<0, false, false><<<grid, blk, kAttnSmemX2, st>>>(tmQ, tmK, tmV, p);
-    MV_CHECK_LAUNCH("attention_fwd_k128x2_kernel");
-    return MV_OK;
-  }
-  if (kstep == 128 || p.trace != nullptr) {
-    const int stale = kn.stale;   // 1: exponentials use the previous step's reference (row max off the critical path)
+  if (kstep == 128) {
+    const int stale = kn.stale;   // 1 (default): fixed-reference softmax, no per-step row max
     if (stale && !p.pingpong && emu <= 1 && softmax_scale > 0.f) {
       if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else if (emu == 1) attention_fwd_k128_kernel<1, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);

@@ -55,7 +55,7 @@ _SIGNATURES = {
     "mv_linear_f32_vec": [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _ptr],
     "mv_sinusoid_embed": [_ptr, _int, _ptr, _int, _ptr],
     "mv_attention_fwd_trace": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr, _int, _ptr],
-    "mv_attention_config": [_int, _int, _int, _int, _int, _int],
+    "mv_attention_config": [_int, _int, _int, _int, _int],
     "mv_t5_attention": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _int, _ptr],
     "mv_t5_rmsnorm": [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _f32, _ptr],
     "mv_embed_gather": [_ptr, _i64, _i64, _ptr, _ptr, _i64, _int, _int, _ptr],
@@ -455,7 +455,6 @@ def attention_trace(q, k, v, out, trace, softmax_scale=None):
     return out
 
 
-def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, split=-1, skew=-1):
+def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, skew=-1):
     """Diagnostics: pick the attention kernel variant for subsequent launches (negative = keep); tools/ab_step.py."""
-    _check(lib().mv_attention_config(int(kstep), int(emu), int(stale), int(pingpong), int(split), int(skew)),
-           "mv_attention_config")
+    _check(lib().mv_attention_config(int(kstep), int(emu), int(stale), int(pingpong), int(skew)), "mv_attention_config")

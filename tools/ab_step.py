@@ -1,7 +1,7 @@
 """In-step A/B of the attention kernel variants on the real 14B 720P forward (one process, one model build).
 For every variant: 1 untimed forward, then 2 timed forwards (= the DiT part of one denoising step) with per-launch
 CUDA-event timing of the self-attention kernel; SM clock / power sampled with nvidia-smi while timing.
-Usage: python tools/ab_step.py [workload] [variant ...]   variant = kstep:emu:stale:pingpong[:split[:skew]]  (default list below)"""
+Usage: python tools/ab_step.py [workload] [variant ...]   variant = kstep:emu:stale:pingpong[:skew]  (default list below)"""
 import json
 import os
 import sys
@@ -21,7 +21,7 @@ from wan.modules.model import WanModel  # noqa: E402
 def main():
     args = sys.argv[1:]
     workload = args[0] if args and args[0] in bench.WORKLOADS else "720p"
-    variants = [a for a in args if ":" in a] or ["64:1:0:0", "128:0:0:0", "128:0:1:0", "128:1:1:0", "128:0:0:1"]
+    variants = [a for a in args if ":" in a] or ["128:0:1:0", "128:0:0:0", "64:1:0:0", "128:0:1:0"]
     dev = torch.device("cuda", 0)
     mv.device_check()
     cfg = Config(t2v_14B)
@@ -41,8 +41,8 @@ def main():
     t = torch.tensor([900], device=dev)
     ref = None
     for var in variants:
-        ks, emu, stale, pp, split, skew = (int(x) for x in (var.split(":") + ["0", "0"])[:6])
-        mv.attention_config(ks, emu, stale, pp, split, skew)
+        ks, emu, stale, pp, skew = (int(x) for x in (var.split(":") + ["0"])[:5])
+        mv.attention_config(ks, emu, stale, pp, skew)
         out = model([lat], t=t, context=ctx, seq_len=seq_len)[0]
         torch.cuda.synchronize()
         sampler = bench.ClockSampler(0)
