@@ -695,6 +695,7 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         uint32_t pk[2][32];
         float2 sum2;
         bool redo;
+        int redone = 0;   // warp-uniform
 #pragma unroll 1
         do {
           const float2 sc2 = make_float2(sl2, sl2);
@@ -723,6 +724,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           // overflow guard on the sum (inf included; !(x <= t) also catches NaN)
           redo = __any_sync(0xffffffffu, !(sum2.x + sum2.y <= 1.8446744073709552e19f));   // 2^64
           if (redo) {
+            if (redone++ > 0) break;   // still not finite with the exact row max as reference: the INPUT holds inf / NaN.
+                                       // Let it propagate into this row's output (as the classic loop does); never spin.
             load_scores();                                     // the scores are still in TMEM: P has not been stored yet
             rescale_by(fmaxf(row_max() * sl2 - ref2, 0.f));    // exact reference; the second pass cannot overflow
           }

@@ -43,19 +43,19 @@ def fixed_reference_attention(q, k, v, scale, step=128, warp_rows=32):
             vt[:w] = v[j * step:j * step + w]
             if j == 0:
                 ref2 = (s.max(1) * sl2).astype(np.float32)
-            while True:
+            for attempt in range(2):                 # at most ONE redo: with the exact max nothing finite overflows
                 with np.errstate(over="ignore", invalid="ignore"):
                     e = np.exp2((s * sl2 - ref2[:, None]).astype(np.float32)).astype(np.float32)
                     row_sum = e.sum(1, dtype=np.float32)
-                if np.any(~(row_sum <= GUARD)):      # warp vote; !(x <= t) also catches inf / NaN
-                    n_redo += 1
-                    up = np.maximum(s.max(1) * sl2 - ref2, 0).astype(np.float32)
-                    alpha = np.exp2(-up).astype(np.float32)
-                    l *= alpha
-                    acc *= alpha[:, None]
-                    ref2 = (ref2 + up).astype(np.float32)
-                    continue
-                break
+                if attempt == 1 or not np.any(~(row_sum <= GUARD)):   # warp vote; !(x <= t) also catches inf / NaN
+                    break
+                n_redo += 1
+                with np.errstate(invalid="ignore"):
+                    up = np.maximum(np.fmax.reduce(s, axis=1) * sl2 - ref2, 0).astype(np.float32)   # max.f32 skips NaN
+                alpha = np.exp2(-up).astype(np.float32)
+                l *= alpha
+                acc *= alpha[:, None]
+                ref2 = (ref2 + up).astype(np.float32)
             l += row_sum
             acc += _bf16(e) @ vt                      # P is rounded to bf16 before P.V, the sum is not
         out[rows] = acc / l[:, None]
@@ -103,3 +103,15 @@ def test_fixed_reference_matches_on_random_scores():
                                                      v[:, 0].float().numpy(), 0.5)
     assert n_steps == 3
     assert _rel(out, ref) <= 5e-3
+
+
+def test_fixed_reference_terminates_on_nan_scores():
+    """Non-finite input: one bounded redo, then the NaN propagates into the rows that saw it (never a spin)."""
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(40, 1, 128, generator=g).bfloat16()[:, 0].float().numpy()
+    k = torch.randn(300, 1, 128, generator=g).bfloat16()[:, 0].float().numpy()
+    v = torch.randn(300, 1, 128, generator=g).bfloat16()[:, 0].float().numpy()
+    k[200, 7] = np.nan
+    with np.errstate(invalid="ignore"):
+        out, n_redo, _ = fixed_reference_attention(q, k, v, 128 ** -0.5)
+    assert np.isnan(out).all() and n_redo == 2          # one redo per warp of 32 rows (40 rows = 2 warps)

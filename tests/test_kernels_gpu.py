@@ -93,6 +93,23 @@ def test_attention(mv, Lq, Lk, H):
     assert (out.float().cpu() - ref).abs().max().item() <= 2e-2
 
 
+def test_attention_nonfinite_input_terminates(mv):
+    """A NaN key must propagate into the outputs of its head (as in the reference softmax) and nowhere else — and the
+    overflow-guarded redo of the fixed-reference softmax must not spin on it (it is bounded to one exact redo)."""
+    g = torch.Generator().manual_seed(5)
+    Lq, Lk, H = 256, 300, 2
+    q = torch.randn(Lq, H, 128, generator=g).bfloat16()
+    k = torch.randn(Lk, H, 128, generator=g).bfloat16()
+    v = torch.randn(Lk, H, 128, generator=g).bfloat16()
+    k[200, 0, 7] = float("nan")
+    ref = O.attention(q[:, 1:], k[:, 1:], v[:, 1:], O.bf16_rt)
+    out = torch.zeros(Lq, H, 128, dtype=torch.bfloat16, device=DEV)
+    mv.attention(q.to(DEV), k.to(DEV), v.to(DEV), out)
+    torch.cuda.synchronize()
+    assert torch.isnan(out[:, 0].float()).all()
+    assert rel_l2(out[:, 1:].float(), ref) <= 5e-3
+
+
 @pytest.mark.parametrize("Lq,Lk,H,n_dst", [(301, 333, 2, 2), (1024, 512, 3, 4)])
 def test_attention_scatter_epilogue(mv, Lq, Lk, H, n_dst):
     """mv_attention_fwd_scatter (the fused Ulysses return path): query row r is stored into destination
