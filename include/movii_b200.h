@@ -94,6 +94,34 @@ int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, const float* 
 int mv_qkv_prepare(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16, int sp_world,
                    int M, int C, int head_dim, float eps, mv_stream_t stream);
 
+/* q, k (and, when scattering, v) of a fused QKV row [M, 3C] (row stride ld) in ONE launch: full-row WanRMSNorm with
+ * gain_q / gain_k + RoPE (cs != NULL) on the q and k column slabs [0,C) and [C,2C) — what model.py:139-148 does with
+ * five ATen launches per tensor.  n_dst == 0: in place (v untouched).  n_dst > 0 (Ulysses, xdit_context_parallel.py:
+ * 169-190): head group d of local row m of q / k / v is stored to dst_x[d] + (src_slot*M + m)*(C/n_dst), i.e. into
+ * slab `src_slot` of destination d's [slot][M][C/n_dst] buffer — local send buffers (NCCL mode: dst_x[d] = base +
+ * d*M*(C/n_dst), src_slot = 0) or NVLink-mapped peer receive buffers (src_slot = this rank). */
+int mv_qkv_norm_rope(void* qkv_bf16, int64_t ld, const float* gain_q, const float* gain_k, const float* cs, int M, int C,
+                     int head_dim, float eps, void* const* dst_q, void* const* dst_k, void* const* dst_v, int n_dst,
+                     int src_slot, mv_stream_t stream);
+
+/* Classifier-free guidance + one FlowUniPC multistep update in a single pass over the latent
+ * (wan/text2video.py:245-254; wan/utils/fm_solvers_unipc.py:319-332,351-485,487-627):
+ *   noise = uncond + guide*(cond - uncond);  x0 = sample - sigma*noise;
+ *   corrected = UniC(last_sample, history, x0)   (when use_corrector);   prev = UniP(corrected, x0, history)
+ * hist0/1/2 = model_outputs[-1/-2/-3] BEFORE this step (NULL when unused).  coef: MV_UNIPC_NCOEF host floats
+ * {guide, sigma, use_corrector, c_order, c_ratio, c_a, c_b, c_rho_last, c_rk0, c_rk1, c_rho0, c_rho1,
+ *  p_order, p_ratio, p_a, p_b, p_rk0, p_rk1, p_rho0, p_rho1} computed by the scheduler on the host exactly as the
+ * reference does.  Outputs: x0_out (new model_outputs[-1]), sample_out (corrected sample = next last_sample),
+ * prev_out (next latent).  Element-wise fp32 in the reference's operation order (bit-identical to the ATen chain). */
+#define MV_UNIPC_NCOEF 20
+int mv_unipc_cfg_step(const float* cond, const float* uncond, const float* sample, const float* last_sample,
+                      const float* hist0, const float* hist1, const float* hist2, float* x0_out, float* sample_out,
+                      float* prev_out, int64_t n, const float* coef, int ncoef, mv_stream_t stream);
+
+/* out[l, :] = mods[l, :] + e0[:], fp32: the per-layer `modulation + e` tables of all blocks (model.py:292-295) or of
+ * the head (:341) in one launch. */
+int mv_modulation_table(const float* mods, const float* e0, float* out, int layers, int len, mv_stream_t stream);
+
 /* A_bf16[L, C*ph*pw] <- latent fp32 [C, F, H, W], patch (1,ph,pw); column = c*ph*pw + i*pw + j, the
  * flatten(1) order of patch_embedding.weight (model.py:445-450,529-533). */
 int mv_patchify(const float* latent, void* a_bf16, int C, int F, int H, int W, int ph, int pw,

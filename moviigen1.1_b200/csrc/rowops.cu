@@ -2,6 +2,7 @@
 // patchify gather, fp32 head + unpatchify, fp32 time-embedding GEMV, sinusoidal embedding.
 // Each replaces a chain of ATen elementwise launches in wan/modules/model.py (cited per kernel).
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -91,89 +92,158 @@ ln_modulate_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
 }
 
 // --------------------------------------------------------------------------------------------
-// WanRMSNorm over the full row + RoPE, in place on bf16.             model.py:70-86, 39-67
-// One CTA per row; 8 bf16 (one uint4) per thread per step.
+// q / k / (v) of one fused QKV row in ONE launch: full-row WanRMSNorm (+ RoPE) per part, optional Ulysses head
+// scatter of all parts (model.py:139-151; xdit_context_parallel.py:169-190).
+// One WARP per (row, part): the row part (C bf16) lives in the warp's registers (NV uint4 per lane), the sum of
+// squares is a shuffle reduction (no __syncthreads), every lane keeps NV independent 16-byte loads in flight.
+// Replaces three launches of rmsnorm_rope_kernel (one CTA per row, 62 % lane use at C = 5120) per layer.
 // --------------------------------------------------------------------------------------------
-constexpr int kRmsVec = 4;  // uint4 per thread -> C <= 256*8*4 = 8192
-
-// When `out` is given the result is written out of place in the Ulysses send layout
-// out[dst][row][c'] with dst = col / (C / sp_world), c' = col % (C / sp_world) (rows = gridDim.x), i.e. the
-// head-scatter of xdit_context_parallel.py:185-190 is fused into this pass.  weight == nullptr skips the
-// norm (plain scatter copy, used for V).
-struct ScatterTable {
-  __nv_bfloat16* dst[8];  // per destination rank: base of its receive buffer [src rank][rows][C / sp_world]
-  int n;                  // 0: no table (use `out`), else sp_world
-  int src_rank;
+struct NormPart {
+  const float* weight;        // RMSNorm gain [C] or null (plain copy: V)
+  int rope;                   // apply the cos/sin table
+  int col0;                   // column offset of this part inside the row (elements)
+  __nv_bfloat16* dst[8];      // scatter: base of destination d's slab for THIS source rank, [rows][C / n_dst];
+                              // dst[0] == null: in place
+};
+struct NormArgs {
+  NormPart part[3];
+  int nparts;
+  int n_dst;                  // 0: in place; else number of head groups (= sequence-parallel ranks)
 };
 
-// With a ScatterTable the head group of destination rank d is stored straight into rank d's HBM (a peer pointer
-// mapped over NVLink): the all-to-all of xdit_context_parallel.py:185-190 happens inside this pass.
-__global__ void __launch_bounds__(kRowThreads)
-rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ weight,
-                    const float* __restrict__ cs, int C, int head_dim, float eps,
-                    __nv_bfloat16* __restrict__ out, int sp_world, const ScatterTable tab) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
-  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
+template <int NV>
+__global__ void __launch_bounds__(256)
+qkv_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ cs, int M, int C,
+                     int head_dim, float eps, const NormArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (item >= static_cast<int64_t>(M) * a.nparts) return;   // warp-uniform
+  const int row = static_cast<int>(item / a.nparts);
+  const int pi = static_cast<int>(item - static_cast<int64_t>(row) * a.nparts);
+  const NormPart& pt = a.part[pi];
+  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + pt.col0);
   const int nvec = C >> 3;
-  uint4 v[kRmsVec];
+  uint4 v[NV];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < kRmsVec; ++i) {
-    const int idx = threadIdx.x + i * kRowThreads;
-    if (idx < nvec) {
-      v[i] = xr[idx];
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < nvec) v[i] = xr[idx];
+  }
+  const float* w = pt.weight;
+  float rinv = 1.f;
+  if (w != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float a = bf16_lo(u[k]), bb = bf16_hi(u[k]);
-        ss += a * a + bb * bb;
+        const float lo = bf16_lo(u[k]), hi = bf16_hi(u[k]);
+        ss += lo * lo + hi * hi;
       }
     }
+    rinv = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
   }
-  const float rinv = weight != nullptr ? rsqrtf(block_sum(ss, red) / static_cast<float>(C) + eps) : 1.f;
-  const int half = head_dim >> 1;
-  const int cols_per_rank = C / sp_world;
-  const int rows_total = gridDim.x;
-  const float* csr = cs != nullptr ? cs + static_cast<int64_t>(row) * head_dim : nullptr;  // [half][2]
+  const float* csr = (pt.rope && cs != nullptr) ? cs + static_cast<int64_t>(row) * head_dim : nullptr;  // [half][2]
+  const int cols_per_dst = a.n_dst > 0 ? C / a.n_dst : C;
 #pragma unroll
-  for (int i = 0; i < kRmsVec; ++i) {
-    const int idx = threadIdx.x + i * kRowThreads;
-    if (idx < nvec) {
-      const int col = idx << 3;
-      uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      if (weight != nullptr) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col) + 1);
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx >= nvec) continue;
+    const int col = idx << 3;
+    uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    if (w != nullptr) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + col) + 1);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float c4[8];
+      if (csr != nullptr) {
+        const float4* cp = reinterpret_cast<const float4*>(csr + (col % head_dim));   // 4 (cos, sin) pairs
+        const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+        c4[0] = c0.x; c4[1] = c0.y; c4[2] = c0.z; c4[3] = c0.w; c4[4] = c1.x; c4[5] = c1.y; c4[6] = c1.z; c4[7] = c1.w;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        // (x.float() * rsqrt(..)).type_as(x) * weight     -> bf16 rounding before the fp32 weight
-        float a = bf16_round(bf16_lo(u[k]) * rinv) * wv[2 * k];
-        float bb = bf16_round(bf16_hi(u[k]) * rinv) * wv[2 * k + 1];
+        // (x.float() * rsqrt(..)).type_as(x) * weight     -> bf16 rounding before the fp32 weight (model.py:83-86)
+        float p0 = bf16_round(bf16_lo(u[k]) * rinv) * wv[2 * k];
+        float p1 = bf16_round(bf16_hi(u[k]) * rinv) * wv[2 * k + 1];
         if (csr != nullptr) {
-          const int pair = ((col + 2 * k) % head_dim) >> 1;
-          const float2 c2 = __ldg(reinterpret_cast<const float2*>(csr) + pair);
-          const float ra = a * c2.x - bb * c2.y;
-          const float rb = a * c2.y + bb * c2.x;
-          a = ra;
-          bb = rb;
+          const float r0 = p0 * c4[2 * k] - p1 * c4[2 * k + 1];
+          const float r1 = p0 * c4[2 * k + 1] + p1 * c4[2 * k];
+          p0 = r0;
+          p1 = r1;
         }
-        u[k] = pack_bf16(a, bb);
-      }
-      }
-      (void)half;
-      if (out == nullptr && tab.n == 0) {
-        xr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
-      } else {
-        const int dst = col / cols_per_rank, cc = col - dst * cols_per_rank;
-        __nv_bfloat16* base = tab.n > 0 ? tab.dst[dst] : out;
-        const int slot = tab.n > 0 ? tab.src_rank : dst;
-        uint4* o = reinterpret_cast<uint4*>(base + (static_cast<int64_t>(slot) * rows_total + row) * cols_per_rank + cc);
-        *o = make_uint4(u[0], u[1], u[2], u[3]);
+        u[k] = pack_bf16(p0, p1);
       }
     }
+    if (a.n_dst == 0) {
+      if (w != nullptr) xr[idx] = make_uint4(u[0], u[1], u[2], u[3]);
+    } else {
+      const int d = col / cols_per_dst, cc = col - d * cols_per_dst;
+      uint4* o = reinterpret_cast<uint4*>(pt.dst[d] + static_cast<int64_t>(row) * cols_per_dst + cc);
+      *o = make_uint4(u[0], u[1], u[2], u[3]);
+    }
   }
+}
+
+// --------------------------------------------------------------------------------------------
+// Classifier-free guidance + one UniPC multistep update, all latent-sized arithmetic of a sampling step in one
+// pass (text2video.py:245-254; fm_solvers_unipc.py:319-332 convert_model_output, :487-627 corrector, :351-485
+// predictor).  The scalar coefficients are computed on the host exactly as the reference
+// does (its sigmas live on the CPU); the element-wise operations are issued in the reference's order with
+// explicitly rounded fp32 operations (no FMA contraction), so the result equals the chain of ATen kernels.
+// --------------------------------------------------------------------------------------------
+struct UniPCArgs {
+  float guide;                 // noise = uncond + guide * (cond - uncond)
+  float sigma;                 // x0 = sample - sigma * noise
+  int use_corrector, c_order;  // corrector (UniC) of order c_order on (last_sample, history, x0)
+  float c_ratio, c_a, c_b, c_rho_last, c_rk[2], c_rho[2];
+  int p_order;                 // predictor (UniP) of order p_order
+  float p_ratio, p_a, p_b, p_rk[2], p_rho[2];
+};
+
+__global__ void __launch_bounds__(256)
+unipc_cfg_step_kernel(const float* cond, const float* uncond, const float* sample, const float* last_sample,
+                      const float* h0, const float* h1, const float* h2, float* x0_out, float* sample_out,
+                      float* prev_out, int64_t n, const UniPCArgs a) {   // no __restrict__: outputs may alias inputs
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float c = cond[i], u = uncond[i];
+    const float noise = __fadd_rn(u, __fmul_rn(a.guide, __fsub_rn(c, u)));
+    float s = sample[i];
+    const float x0 = __fsub_rn(s, __fmul_rn(a.sigma, noise));
+    const float m0 = h0 != nullptr ? h0[i] : 0.f;      // model_outputs[-1] before this step
+    const float m1 = h1 != nullptr ? h1[i] : 0.f;      // model_outputs[-2]
+    const float m2 = h2 != nullptr ? h2[i] : 0.f;      // model_outputs[-3]
+    if (a.use_corrector) {
+      const float xt = __fsub_rn(__fmul_rn(a.c_ratio, last_sample[i]), __fmul_rn(a.c_a, m0));
+      float res = __fmul_rn(__fsub_rn(x0, m0), a.c_rho_last);
+      if (a.c_order >= 2) res = __fadd_rn(res, __fmul_rn(__fdiv_rn(__fsub_rn(m1, m0), a.c_rk[0]), a.c_rho[0]));
+      if (a.c_order >= 3) res = __fadd_rn(res, __fmul_rn(__fdiv_rn(__fsub_rn(m2, m0), a.c_rk[1]), a.c_rho[1]));
+      s = __fsub_rn(xt, __fmul_rn(a.c_b, res));
+    }
+    // predictor: history is now (x0, m0, m1)
+    float xn = __fsub_rn(__fmul_rn(a.p_ratio, s), __fmul_rn(a.p_a, x0));
+    if (a.p_order >= 2) {
+      float res = __fmul_rn(__fdiv_rn(__fsub_rn(m0, x0), a.p_rk[0]), a.p_rho[0]);
+      if (a.p_order >= 3) res = __fadd_rn(res, __fmul_rn(__fdiv_rn(__fsub_rn(m1, x0), a.p_rk[1]), a.p_rho[1]));
+      xn = __fsub_rn(xn, __fmul_rn(a.p_b, res));
+    }
+    x0_out[i] = x0;
+    sample_out[i] = s;
+    prev_out[i] = xn;
+  }
+}
+
+// out[l, :] = mods[l, :] + e0[:]  (per-layer adaLN table `modulation + e`, model.py:292-295 / :341), fp32
+__global__ void __launch_bounds__(256)
+modulation_table_kernel(const float* __restrict__ mods, const float* __restrict__ e0, float* __restrict__ out,
+                        int layers, int len) {
+  const int64_t total = static_cast<int64_t>(layers) * len;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = mods[i] + e0[i % len];
 }
 
 // --------------------------------------------------------------------------------------------
@@ -390,54 +460,178 @@ extern "C" int mv_ln_modulate(const float* x, int64_t ldx, const float* shift, c
   return MV_OK;
 }
 
-extern "C" int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, const float* cs, int M, int C,
-                               int head_dim, float eps, mv_stream_t stream) {
-  return mv_qkv_prepare(x_bf16, ld, weight, cs, nullptr, 1, M, C, head_dim, eps, stream);
-}
-
-static int qkv_prepare_impl(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16,
-                            void* const* dst_ptrs, int src_rank, int sp_world, int M, int C, int head_dim, float eps,
-                            mv_stream_t stream) {
+// Launches qkv_norm_rope_kernel for up to three row parts.
+static int launch_norm_parts(void* x_bf16, int64_t ld, const float* cs, int M, int C, int head_dim, float eps,
+                             const NormArgs& a, mv_stream_t stream, const char* who) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
-  MV_REQUIRE(M > 0 && C > 0, "mv_rmsnorm_rope: empty problem");
-  MV_REQUIRE(sp_world >= 1 && sp_world <= 8 && C % sp_world == 0 && (C / sp_world) % head_dim == 0,
-             "mv_qkv_prepare: C=%d is not divisible into %d head groups", C, sp_world);
-  MV_REQUIRE(out_bf16 != nullptr || dst_ptrs != nullptr || sp_world == 1, "mv_qkv_prepare: scatter needs an output buffer");
-  MV_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "mv_qkv_prepare: out must be 16B aligned");
-  MV_REQUIRE(C % 8 == 0 && C <= kRowThreads * 8 * kRmsVec, "mv_rmsnorm_rope: C=%d must be a multiple of 8 and <= %d", C,
-             kRowThreads * 8 * kRmsVec);
-  MV_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "mv_rmsnorm_rope: rows must be 16B aligned");
-  MV_REQUIRE(head_dim > 0 && head_dim % 2 == 0 && C % head_dim == 0, "mv_rmsnorm_rope: bad head_dim %d", head_dim);
-  ScatterTable tab;
-  tab.n = 0;
-  tab.src_rank = src_rank;
-  for (int i = 0; i < 8; ++i) tab.dst[i] = nullptr;
-  if (dst_ptrs != nullptr) {
-    MV_REQUIRE(src_rank >= 0 && src_rank < sp_world, "mv_qkv_prepare_p2p: bad source rank");
-    tab.n = sp_world;
-    for (int i = 0; i < sp_world; ++i) {
-      MV_REQUIRE(dst_ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(dst_ptrs[i]) & 15) == 0,
-                 "mv_qkv_prepare_p2p: destination %d is null or misaligned", i);
-      tab.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst_ptrs[i]);
-    }
+  MV_REQUIRE(M > 0 && C > 0, "%s: empty problem", who);
+  MV_REQUIRE(C % 8 == 0 && C <= 8192, "%s: C=%d must be a multiple of 8 and <= 8192", who, C);
+  MV_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "%s: rows must be 16B aligned", who);
+  MV_REQUIRE(head_dim >= 8 && head_dim % 8 == 0 && C % head_dim == 0, "%s: bad head_dim %d", who, head_dim);
+  MV_REQUIRE((reinterpret_cast<uintptr_t>(cs) & 15) == 0, "%s: cos/sin table must be 16B aligned", who);
+  MV_REQUIRE(a.n_dst >= 0 && a.n_dst <= 8, "%s: at most 8 destinations", who);
+  if (a.n_dst > 0) {
+    MV_REQUIRE(C % a.n_dst == 0 && (C / a.n_dst) % head_dim == 0, "%s: C=%d is not divisible into %d head groups", who, C,
+               a.n_dst);
+    for (int p = 0; p < a.nparts; ++p)
+      for (int d = 0; d < a.n_dst; ++d)
+        MV_REQUIRE(a.part[p].dst[d] != nullptr && (reinterpret_cast<uintptr_t>(a.part[p].dst[d]) & 15) == 0,
+                   "%s: destination %d of part %d is null or misaligned", who, d, p);
   }
-  rmsnorm_rope_kernel<<<M, kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(x_bf16), ld, weight, cs, C, head_dim, eps,
-      reinterpret_cast<__nv_bfloat16*>(out_bf16), sp_world, tab);
-  MV_CHECK_LAUNCH("rmsnorm_rope_kernel");
+  for (int p = 0; p < a.nparts; ++p)
+    MV_REQUIRE(a.part[p].col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.part[p].weight) & 15) == 0,
+               "%s: part %d misaligned", who, p);
+  const int64_t warps = static_cast<int64_t>(M) * a.nparts;
+  const int64_t blocks = (warps + 7) / 8;
+  MV_REQUIRE(blocks < (1ll << 31), "%s: too many rows", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* x = reinterpret_cast<__nv_bfloat16*>(x_bf16);
+  const int nv = (C / 8 + 31) / 32;
+  const int g = static_cast<int>(blocks);
+  if (nv <= 4) qkv_norm_rope_kernel<4><<<g, 256, 0, st>>>(x, ld, cs, M, C, head_dim, eps, a);
+  else if (nv <= 8) qkv_norm_rope_kernel<8><<<g, 256, 0, st>>>(x, ld, cs, M, C, head_dim, eps, a);
+  else if (nv <= 20) qkv_norm_rope_kernel<20><<<g, 256, 0, st>>>(x, ld, cs, M, C, head_dim, eps, a);
+  else qkv_norm_rope_kernel<32><<<g, 256, 0, st>>>(x, ld, cs, M, C, head_dim, eps, a);
+  MV_CHECK_LAUNCH("qkv_norm_rope_kernel");
   return MV_OK;
+}
+
+static NormArgs one_part(const float* weight, const float* cs) {
+  NormArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nparts = 1;
+  a.part[0].weight = weight;
+  a.part[0].rope = cs != nullptr ? 1 : 0;
+  return a;
+}
+
+extern "C" int mv_rmsnorm_rope(void* x_bf16, int64_t ld, const float* weight, const float* cs, int M, int C,
+                               int head_dim, float eps, mv_stream_t stream) {
+  if (weight == nullptr) {
+    set_error("mv_rmsnorm_rope: weight is required");
+    return MV_E_SHAPE;
+  }
+  return launch_norm_parts(x_bf16, ld, cs, M, C, head_dim, eps, one_part(weight, cs), stream, "mv_rmsnorm_rope");
 }
 
 extern "C" int mv_qkv_prepare(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* out_bf16,
                               int sp_world, int M, int C, int head_dim, float eps, mv_stream_t stream) {
-  return qkv_prepare_impl(x_bf16, ld, weight, cs, out_bf16, nullptr, 0, sp_world, M, C, head_dim, eps, stream);
+  NormArgs a = one_part(weight, cs);
+  if (out_bf16 != nullptr) {
+    if (sp_world < 1 || sp_world > 8 || C % sp_world != 0) {
+      set_error("mv_qkv_prepare: bad sp_world %d for C=%d", sp_world, C);
+      return MV_E_SHAPE;
+    }
+    a.n_dst = sp_world;   // out[dst][row][C / sp_world]
+    for (int d = 0; d < sp_world; ++d)
+      a.part[0].dst[d] = reinterpret_cast<__nv_bfloat16*>(out_bf16) + static_cast<int64_t>(d) * M * (C / sp_world);
+  } else if (weight == nullptr) {
+    set_error("mv_qkv_prepare: nothing to do (no weight and no output)");
+    return MV_E_SHAPE;
+  }
+  return launch_norm_parts(x_bf16, ld, cs, M, C, head_dim, eps, a, stream, "mv_qkv_prepare");
 }
 
 extern "C" int mv_qkv_prepare_p2p(void* x_bf16, int64_t ld, const float* weight, const float* cs, void* const* dst_ptrs,
                                   int src_rank, int sp_world, int M, int C, int head_dim, float eps,
                                   mv_stream_t stream) {
-  return qkv_prepare_impl(x_bf16, ld, weight, cs, nullptr, dst_ptrs, src_rank, sp_world, M, C, head_dim, eps, stream);
+  if (dst_ptrs == nullptr || sp_world < 1 || sp_world > 8 || src_rank < 0 || src_rank >= sp_world || C % sp_world != 0) {
+    set_error("mv_qkv_prepare_p2p: bad destination table / rank %d of %d", src_rank, sp_world);
+    return MV_E_SHAPE;
+  }
+  NormArgs a = one_part(weight, cs);
+  a.n_dst = sp_world;     // dst_ptrs[d][src_rank][row][C / sp_world]
+  for (int d = 0; d < sp_world; ++d)
+    a.part[0].dst[d] = dst_ptrs[d] == nullptr ? nullptr
+                       : reinterpret_cast<__nv_bfloat16*>(dst_ptrs[d]) + static_cast<int64_t>(src_rank) * M * (C / sp_world);
+  return launch_norm_parts(x_bf16, ld, cs, M, C, head_dim, eps, a, stream, "mv_qkv_prepare_p2p");
+}
+
+extern "C" int mv_qkv_norm_rope(void* qkv_bf16, int64_t ld, const float* gain_q, const float* gain_k, const float* cs,
+                                int M, int C, int head_dim, float eps, void* const* dst_q, void* const* dst_k,
+                                void* const* dst_v, int n_dst, int src_slot, mv_stream_t stream) {
+  if (gain_q == nullptr || gain_k == nullptr) {
+    set_error("mv_qkv_norm_rope: both gains are required");
+    return MV_E_SHAPE;
+  }
+  NormArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nparts = n_dst > 0 ? 3 : 2;
+  a.n_dst = n_dst;
+  a.part[0].weight = gain_q;
+  a.part[1].weight = gain_k;
+  a.part[0].rope = a.part[1].rope = cs != nullptr ? 1 : 0;
+  for (int p = 0; p < 3; ++p) a.part[p].col0 = p * C;
+  if (n_dst > 0) {
+    if (n_dst > 8 || dst_q == nullptr || dst_k == nullptr || dst_v == nullptr || src_slot < 0 || C % n_dst != 0) {
+      set_error("mv_qkv_norm_rope: bad destination tables (n_dst=%d)", n_dst);
+      return MV_E_SHAPE;
+    }
+    void* const* tabs[3] = {dst_q, dst_k, dst_v};
+    for (int p = 0; p < 3; ++p)
+      for (int d = 0; d < n_dst; ++d)
+        a.part[p].dst[d] = tabs[p][d] == nullptr ? nullptr
+                           : reinterpret_cast<__nv_bfloat16*>(tabs[p][d]) + static_cast<int64_t>(src_slot) * M * (C / n_dst);
+  }
+  return launch_norm_parts(qkv_bf16, ld, cs, M, C, head_dim, eps, a, stream, "mv_qkv_norm_rope");
+}
+
+extern "C" int mv_unipc_cfg_step(const float* cond, const float* uncond, const float* sample, const float* last_sample,
+                                 const float* hist0, const float* hist1, const float* hist2, float* x0_out,
+                                 float* sample_out, float* prev_out, int64_t n, const float* coef, int ncoef,
+                                 mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(n > 0 && cond != nullptr && uncond != nullptr && sample != nullptr && x0_out != nullptr &&
+             sample_out != nullptr && prev_out != nullptr, "mv_unipc_cfg_step: null tensor / empty problem");
+  MV_REQUIRE(coef != nullptr && ncoef == MV_UNIPC_NCOEF, "mv_unipc_cfg_step: expected %d coefficients, got %d",
+             MV_UNIPC_NCOEF, ncoef);
+  UniPCArgs a;
+  a.guide = coef[0];
+  a.sigma = coef[1];
+  a.use_corrector = coef[2] != 0.f ? 1 : 0;
+  a.c_order = static_cast<int>(coef[3]);
+  a.c_ratio = coef[4];
+  a.c_a = coef[5];
+  a.c_b = coef[6];
+  a.c_rho_last = coef[7];
+  a.c_rk[0] = coef[8];
+  a.c_rk[1] = coef[9];
+  a.c_rho[0] = coef[10];
+  a.c_rho[1] = coef[11];
+  a.p_order = static_cast<int>(coef[12]);
+  a.p_ratio = coef[13];
+  a.p_a = coef[14];
+  a.p_b = coef[15];
+  a.p_rk[0] = coef[16];
+  a.p_rk[1] = coef[17];
+  a.p_rho[0] = coef[18];
+  a.p_rho[1] = coef[19];
+  MV_REQUIRE(a.c_order >= 0 && a.c_order <= 3 && a.p_order >= 1 && a.p_order <= 3, "mv_unipc_cfg_step: orders out of range");
+  MV_REQUIRE(!a.use_corrector || (last_sample != nullptr && hist0 != nullptr && (a.c_order < 2 || hist1 != nullptr) &&
+                                  (a.c_order < 3 || hist2 != nullptr)), "mv_unipc_cfg_step: corrector history missing");
+  MV_REQUIRE((a.p_order < 2 || hist0 != nullptr) && (a.p_order < 3 || hist1 != nullptr),
+             "mv_unipc_cfg_step: predictor history missing");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  unipc_cfg_step_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cond, uncond, sample, last_sample, hist0, hist1, hist2, x0_out, sample_out, prev_out, n, a);
+  MV_CHECK_LAUNCH("unipc_cfg_step_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_modulation_table(const float* mods, const float* e0, float* out, int layers, int len,
+                                   mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(layers > 0 && len > 0 && mods != nullptr && e0 != nullptr && out != nullptr, "mv_modulation_table: bad arguments");
+  const int64_t total = static_cast<int64_t>(layers) * len;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  modulation_table_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(mods, e0, out, layers, len);
+  MV_CHECK_LAUNCH("modulation_table_kernel");
+  return MV_OK;
 }
 
 extern "C" int mv_patchify(const float* latent, void* a_bf16, int C, int F, int H, int W, int ph, int pw,

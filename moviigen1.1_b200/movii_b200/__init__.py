@@ -33,6 +33,9 @@ _SIGNATURES = {
     "mv_rmsnorm_rope": [_ptr, _i64, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
     "mv_gemm_bf16_ksplit": [_ptr, _i64, _i64, _int, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int, _int, _int, _int, _ptr],
     "mv_qkv_prepare": [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _int, _int, _f32, _ptr],
+    "mv_qkv_norm_rope": [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _int, _f32, _ptr, _ptr, _ptr, _int, _int, _ptr],
+    "mv_unipc_cfg_step": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _int, _ptr],
+    "mv_modulation_table": [_ptr, _ptr, _ptr, _int, _int, _ptr],
     "mv_head_tokens": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
     "mv_unpatchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_vae_conv": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
@@ -129,6 +132,11 @@ def _req(t, dtype, name):
         return
     if not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor (movii_b200 has no CPU path)" % name)
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's stream: a tensor on another GPU would be a peer access or a fault
+        raise RuntimeError("%s lives on %s but the current CUDA device is %d: call torch.cuda.set_device(%d) "
+                           "(generate.py:191-200 does) before using movii_b200 on that GPU"
+                           % (name, t.device, torch.cuda.current_device(), t.device.index))
     if t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
 
@@ -188,6 +196,53 @@ def rmsnorm_rope(x, weight, cs=None, head_dim=128, eps=1e-6):
         assert cs.is_contiguous() and cs.shape == (M, head_dim // 2, 2), (cs.shape, M, head_dim)
     _call("mv_rmsnorm_rope", _p(x), x.stride(0), _p(weight), _p(cs), M, C, head_dim, float(eps), _stream())
     return x
+
+
+def qkv_norm_rope(qkv, gain_q, gain_k, cs=None, head_dim=128, eps=1e-6, dst=None, n_dst=0, src_slot=0):
+    """q / k RMSNorm (+ RoPE) of a fused QKV buffer [M, 3C] bf16 in ONE launch.  dst=None: in place.
+    dst=(tab_q, tab_k, tab_v) (ptr_table()s of n_dst slab bases): Ulysses head scatter of q, k and v, see
+    include/movii_b200.h::mv_qkv_norm_rope."""
+    _req(qkv, torch.bfloat16, "qkv"); _req(gain_q, torch.float32, "gain_q"); _req(gain_k, torch.float32, "gain_k")
+    _req(cs, torch.float32, "cs")
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[1] % 3 == 0
+    assert gain_q.is_contiguous() and gain_k.is_contiguous()
+    M, C = qkv.shape[0], qkv.shape[1] // 3
+    if cs is not None:
+        assert cs.is_contiguous() and cs.shape == (M, head_dim // 2, 2), (cs.shape, M, head_dim)
+    tq, tk, tv = dst if dst is not None else (None, None, None)
+    assert (dst is None) == (n_dst == 0)
+    _call("mv_qkv_norm_rope", _p(qkv), qkv.stride(0), _p(gain_q), _p(gain_k), _p(cs), M, C, head_dim, float(eps),
+          tq, tk, tv, int(n_dst), int(src_slot), _stream())
+    return qkv
+
+
+UNIPC_NCOEF = 20
+
+
+def unipc_cfg_step(cond, uncond, sample, last_sample, hist, coef, x0_out, sample_out, prev_out):
+    """Classifier-free guidance + one UniPC update (include/movii_b200.h::mv_unipc_cfg_step).  hist: up to three
+    fp32 tensors (model_outputs[-1], [-2], [-3] before this step) or None entries; coef: UNIPC_NCOEF python floats."""
+    ts = [cond, uncond, sample, last_sample] + list(hist) + [x0_out, sample_out, prev_out]
+    n = cond.numel()
+    for t in ts:
+        _req(t, torch.float32, "latent")
+        assert t is None or (t.is_contiguous() and t.numel() == n)
+    assert len(hist) == 3 and len(coef) == UNIPC_NCOEF
+    arr = (_c.c_float * UNIPC_NCOEF)(*[float(v) for v in coef])
+    _call("mv_unipc_cfg_step", _p(cond), _p(uncond), _p(sample), _p(last_sample), _p(hist[0]), _p(hist[1]), _p(hist[2]),
+          _p(x0_out), _p(sample_out), _p(prev_out), n, arr, UNIPC_NCOEF, _stream())
+    return prev_out
+
+
+def modulation_table(mods, e0, out):
+    """out[l] = mods[l] + e0 (fp32; mods/out [layers, len], e0 [len])."""
+    _req(mods, torch.float32, "mods"); _req(e0, torch.float32, "e0"); _req(out, torch.float32, "out")
+    assert mods.is_contiguous() and e0.is_contiguous() and out.is_contiguous() and out.shape == mods.shape
+    layers = mods.shape[0]
+    ln = mods.numel() // layers
+    assert e0.numel() == ln
+    _call("mv_modulation_table", _p(mods), _p(e0), _p(out), layers, ln, _stream())
+    return out
 
 
 def patchify(latent, out, patch_hw=(2, 2)):

@@ -7,8 +7,8 @@ positions) the heads are scattered / the sequence gathered with an all-to-all, e
 sequence for its 40/P heads, and a second all-to-all brings the outputs back to the token owners.
 
 B200-native realisation here:
-  * the head scatter is fused into the RMSNorm/RoPE pass (mv_qkv_prepare writes the send layout
-    [dst][local token][local heads x 128] directly),
+  * the head scatter of q, k AND v is fused into ONE RMSNorm/RoPE pass over the fused QKV rows (mv_qkv_norm_rope
+    writes the send layout [dst][local token][local heads x 128] directly — or, in p2p mode, the peers' HBM),
   * q, k, v travel as ONE grouped NCCL operation (3 all_to_all_single calls inside a coalescing group are
     pairwise send/recv over NVLink 5 / NVSwitch),
   * attention output is produced directly in the return send layout ([dst][token][heads x 128] is just the
@@ -154,9 +154,10 @@ def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, att
         st = grp.p2p_buffers(mv, rows, C, ws.qkv.device)
     if grp.mode == "p2p" and prepare is None and attend is None:
         qkv = ws.qkv[:rows]
-        mv.qkv_prepare_p2p(qkv[:, 0:C], bw.g_q, cs, st["tab"][0], grp.rank, P, 128, bw.eps)
-        mv.qkv_prepare_p2p(qkv[:, C:2 * C], bw.g_k, cs, st["tab"][1], grp.rank, P, 128, bw.eps)
-        mv.qkv_prepare_p2p(qkv[:, 2 * C:3 * C], None, None, st["tab"][2], grp.rank, P, 128, bw.eps)
+        # ONE pass over the local QKV rows: q/k RMSNorm + RoPE, and the head groups of q, k and v stored straight
+        # into slab `rank` of every destination's receive buffers
+        mv.qkv_norm_rope(qkv, bw.g_q, bw.g_k, cs, 128, bw.eps, dst=(st["tab"][0], st["tab"][1], st["tab"][2]),
+                         n_dst=P, src_slot=grp.rank)
         grp.p2p_barrier(mv, st)                    # all q/k/v slabs complete everywhere
         L = P * rows
         hd = C // bw.num_heads
@@ -167,11 +168,16 @@ def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, att
         grp.p2p_barrier(mv, st)                    # all o slabs complete; also fences q/k/v reuse by the next layer
         return st["o_r"]
     b = grp.buffers(rows, C, ws.qkv.device, ws.qkv.dtype)
-    prepare = prepare or (lambda x, w, c, out: mv.qkv_prepare(x, w, c, out, P, 128, bw.eps))
     qkv = ws.qkv[:rows]
-    prepare(qkv[:, 0:C], bw.g_q, cs, b["q_s"])
-    prepare(qkv[:, C:2 * C], bw.g_k, cs, b["k_s"])
-    prepare(qkv[:, 2 * C:3 * C], None, None, b["v_s"])
+    if prepare is None:
+        # one launch: normalise + rotate q, k and write the send layout [dst][row][C/P] of all three tensors
+        if "tabs" not in b:
+            b["tabs"] = tuple(mv.ptr_table([b[n][d].data_ptr() for d in range(P)]) for n in ("q_s", "k_s", "v_s"))
+        mv.qkv_norm_rope(qkv, bw.g_q, bw.g_k, cs, 128, bw.eps, dst=b["tabs"], n_dst=P, src_slot=0)
+    else:
+        prepare(qkv[:, 0:C], bw.g_q, cs, b["q_s"])
+        prepare(qkv[:, C:2 * C], bw.g_k, cs, b["k_s"])
+        prepare(qkv[:, 2 * C:3 * C], None, None, b["v_s"])
     grp.all_to_all([b["q_r"], b["k_r"], b["v_r"]], [b["q_s"], b["k_s"], b["v_s"]])
     L = P * rows
     q = b["q_r"].view(L, Hl, C // bw.num_heads)

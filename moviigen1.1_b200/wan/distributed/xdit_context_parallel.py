@@ -21,7 +21,35 @@ def usp_dit_forward(self, x, t, context, seq_len, clip_fea=None, y=None, guidanc
 
 
 def usp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16):
-    """WanSelfAttention.forward under SP is fused into the engine's block loop (engine.block_forward with
-    attn_core=sp_self_attention); a standalone per-module call is not a code path of the product."""
-    raise NotImplementedError("usp_attn_forward is executed inside DitEngine.forward_single_sp; "
-                              "call the model's forward (usp_dit_forward) instead")
+    """WanSelfAttention.forward under Ulysses SP as a standalone call (reference: xdit_context_parallel.py:155-198):
+    x [B, L/P, C] is this rank's token shard (already normalised + modulated); q/k/v Linear, full-row RMSNorm, RoPE
+    at the shard's GLOBAL positions (:51-57), head-scatter / sequence-gather exchange, attention over all L keys for
+    40/P heads (the reference does not un-pad here, :178-183), return exchange, o Linear.  Returns [B, L/P, C] bf16.
+    DitEngine.forward_single_sp runs the same launches inside its block loop (engine.block_forward(sp=...))."""
+    from ..modules import engine as E
+    from ..modules.model import _OwnerRef
+    from .ulysses import sp_self_attention
+    mv = E.mv
+    blk = _OwnerRef.get(self)
+    bw = blk._weights()
+    grp = get_sp_group().ulysses
+    B, rows, C = x.shape
+    total = rows * grp.world
+    ws = E.Workspace(rows, C, 8, 8, x.device)
+    outs = []
+    for i in range(B):
+        grid = tuple(int(v) for v in grid_sizes[i].tolist())
+        cs = E.rope_cos_sin(freqs.cpu(), grid, total, grp.rank * rows, rows, x.device)
+        ws.h.copy_(x[i])
+        mv.gemm(ws.h, bw.w_qkv, bw.b_qkv, ws.qkv, mv.MV_EPI_BF16)
+        if grp.world == 1:
+            mv.qkv_norm_rope(ws.qkv, bw.g_q, bw.g_k, cs, 128, bw.eps)
+            E.self_attention_core(ws, rows, total, self.num_heads)
+            y = torch.empty(rows, C, dtype=torch.bfloat16, device=x.device)
+            mv.gemm(ws.attn, bw.w_o, bw.b_o, y, mv.MV_EPI_BF16)
+        else:
+            o_slabs = sp_self_attention(mv, grp, ws, rows, bw, cs, total)
+            y = torch.empty(rows, C, dtype=torch.bfloat16, device=x.device)
+            mv.gemm_ksplit(o_slabs, bw.w_o, bw.b_o, y, mv.MV_EPI_BF16)
+        outs.append(y)
+    return torch.stack(outs)

@@ -26,26 +26,32 @@ def _f32(t):
     return t.detach().to(F32).contiguous()
 
 
+def _bias(t):
+    """Bias of a bf16-autocast Linear: autocast casts every tensor argument of F.linear to bf16, so the value added to
+    the fp32 accumulator is the bf16-rounded bias (kept as fp32 storage for the kernels' epilogues)."""
+    return t.detach().to(BF16).to(F32).contiguous()
+
+
 class BlockWeights:
     """Packed, kernel-ready weights of one WanAttentionBlock (bf16 GEMM operands, fp32 everything else)."""
 
     def __init__(self, blk):
         sa, ca = blk.self_attn, blk.cross_attn
         self.w_qkv = torch.cat([_bf16(sa.q.weight), _bf16(sa.k.weight), _bf16(sa.v.weight)], 0).contiguous()
-        self.b_qkv = torch.cat([_f32(sa.q.bias), _f32(sa.k.bias), _f32(sa.v.bias)], 0).contiguous()
-        self.w_o, self.b_o = _bf16(sa.o.weight), _f32(sa.o.bias)
+        self.b_qkv = torch.cat([_bias(sa.q.bias), _bias(sa.k.bias), _bias(sa.v.bias)], 0).contiguous()
+        self.w_o, self.b_o = _bf16(sa.o.weight), _bias(sa.o.bias)
         self.g_q, self.g_k = _f32(sa.norm_q.weight), _f32(sa.norm_k.weight)
-        self.w_cq, self.b_cq = _bf16(ca.q.weight), _f32(ca.q.bias)
+        self.w_cq, self.b_cq = _bf16(ca.q.weight), _bias(ca.q.bias)
         self.w_ckv = torch.cat([_bf16(ca.k.weight), _bf16(ca.v.weight)], 0).contiguous()
-        self.b_ckv = torch.cat([_f32(ca.k.bias), _f32(ca.v.bias)], 0).contiguous()
-        self.w_co, self.b_co = _bf16(ca.o.weight), _f32(ca.o.bias)
+        self.b_ckv = torch.cat([_bias(ca.k.bias), _bias(ca.v.bias)], 0).contiguous()
+        self.w_co, self.b_co = _bf16(ca.o.weight), _bias(ca.o.bias)
         self.g_cq, self.g_ck = _f32(ca.norm_q.weight), _f32(ca.norm_k.weight)
         if getattr(blk, "cross_attn_norm", True) and hasattr(blk.norm3, "weight") and blk.norm3.weight is not None:
             self.n3_w, self.n3_b = _f32(blk.norm3.weight), _f32(blk.norm3.bias)
         else:
             self.n3_w = self.n3_b = None
-        self.w_1, self.b_1 = _bf16(blk.ffn[0].weight), _f32(blk.ffn[0].bias)
-        self.w_2, self.b_2 = _bf16(blk.ffn[2].weight), _f32(blk.ffn[2].bias)
+        self.w_1, self.b_1 = _bf16(blk.ffn[0].weight), _bias(blk.ffn[0].bias)
+        self.w_2, self.b_2 = _bf16(blk.ffn[2].weight), _bias(blk.ffn[2].bias)
         self.mod = _f32(blk.modulation).view(6, -1)
         self.dim = self.w_o.shape[0]
         self.ffn_dim = self.w_1.shape[0]
@@ -122,8 +128,7 @@ def block_forward(bw, ws, rows, e, cs, ctx, kv_rows, first_block=False, sp=None)
     mv.ln_modulate(x, h, shift=e[0], scale=e[1], eps=eps, round_ln=first_block)
     mv.gemm(h, bw.w_qkv, bw.b_qkv, qkv, mv.MV_EPI_BF16)
     if sp is None or sp.world == 1:
-        mv.rmsnorm_rope(qkv[:, 0:C], bw.g_q, cs, 128, eps)
-        mv.rmsnorm_rope(qkv[:, C:2 * C], bw.g_k, cs, 128, eps)
+        mv.qkv_norm_rope(qkv, bw.g_q, bw.g_k, cs, 128, eps)      # q and k in one launch
         self_attention_core(ws, rows, kv_rows, nh)
         mv.gemm(attn, bw.w_o, bw.b_o, x, mv.MV_EPI_RESID_F32, gate=e[2])
     else:
@@ -180,10 +185,10 @@ class DitEngine:
         self.mods = torch.stack([bw.mod for bw in self.blocks]).contiguous()          # [n_layers, 6, C]
         pe = model.patch_embedding
         self.w_patch = _bf16(pe.weight).flatten(1).contiguous()
-        self.b_patch = _f32(pe.bias)
+        self.b_patch = _bias(pe.bias)
         te = model.text_embedding
-        self.w_t0, self.b_t0 = _bf16(te[0].weight), _f32(te[0].bias)
-        self.w_t2, self.b_t2 = _bf16(te[2].weight), _f32(te[2].bias)
+        self.w_t0, self.b_t0 = _bf16(te[0].weight), _bias(te[0].bias)
+        self.w_t2, self.b_t2 = _bf16(te[2].weight), _bias(te[2].bias)
         tm, tp = model.time_embedding, model.time_projection
         self.w_e0, self.b_e0 = _f32(tm[0].weight), _f32(tm[0].bias)
         self.w_e2, self.b_e2 = _f32(tm[2].weight), _f32(tm[2].bias)
@@ -199,6 +204,8 @@ class DitEngine:
         self.e_hidden = torch.empty(self.dim, dtype=F32, device=dev)
         self.e = torch.empty(self.dim, dtype=F32, device=dev)
         self.e0 = torch.empty(6 * self.dim, dtype=F32, device=dev)
+        self.E = torch.empty_like(self.mods)                    # per-layer (modulation + e0) table of one forward
+        self.em = torch.empty(2, self.dim, dtype=F32, device=dev)
         self.ctx_in = torch.zeros(self.text_len, self.text_dim, dtype=BF16, device=dev)
         self.ctx_h = torch.empty(self.text_len, self.dim, dtype=BF16, device=dev)
         self.ctx = torch.empty(self.text_len, self.dim, dtype=BF16, device=dev)
@@ -262,8 +269,8 @@ class DitEngine:
         return grid, L
 
     def head(self, ws, rows, e, grid, out):
-        em = self.head_mod + e.view(1, -1)                                     # model.py:341
-        mv.head_unpatchify(ws.x[:rows], em[0].contiguous(), em[1].contiguous(), self.w_head, self.b_head, out, grid,
+        em = mv.modulation_table(self.head_mod, e, self.em)                    # model.py:341
+        mv.head_unpatchify(ws.x[:rows], em[0], em[1], self.w_head, self.b_head, out, grid,
                            (self.patch[1], self.patch[2]), self.eps)
 
     # -- WanModel.forward, one sample, P = 1 ----------------------------------------------------------
@@ -275,7 +282,7 @@ class DitEngine:
         e, e0 = self.embed_time(t)
         ctx = self.embed_text(context)
         cs = self.rope_table(freqs, grid, seq_len, 0, seq_len)
-        E = self.mods + e0.unsqueeze(0)                                          # model.py:292-295, all layers
+        E = mv.modulation_table(self.mods, self.e0, self.E).view(len(self.blocks), 6, self.dim)   # model.py:292-295
         for i, bw in enumerate(self.blocks):
             block_forward(bw, ws, seq_len, E[i], cs, ctx, L, first_block=(i == 0))
         C_out = self.out_dim
@@ -297,14 +304,14 @@ class DitEngine:
         e, e0 = self.embed_time(t)
         ctx = self.embed_text(context)
         cs = self.rope_table(freqs, grid, seq_len, start, rows)
-        E = self.mods + e0.unsqueeze(0)
+        E = mv.modulation_table(self.mods, self.e0, self.E).view(len(self.blocks), 6, self.dim)
         for i, bw in enumerate(self.blocks):
             # the reference USP path does not un-pad: all seq_len keys are attended (:178-183 TODO)
             block_forward(bw, ws, rows, E[i], cs, ctx, seq_len, first_block=(i == 0), sp=grp)
-        em = self.head_mod + e.view(1, -1)
+        em = mv.modulation_table(self.head_mod, e, self.em)
         nout = self.w_head.shape[0]
         tok = torch.empty(rows, nout, dtype=F32, device=self.device)
-        mv.head_tokens(ws.x[:rows], em[0].contiguous(), em[1].contiguous(), self.w_head, self.b_head, tok, self.eps)
+        mv.head_tokens(ws.x[:rows], em[0], em[1], self.w_head, self.b_head, tok, self.eps)
         full = grp.all_gather_rows(tok)
         out = torch.empty(self.out_dim, grid[0], grid[1] * self.patch[1], grid[2] * self.patch[2], dtype=F32,
                           device=self.device)

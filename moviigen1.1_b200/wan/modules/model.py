@@ -9,6 +9,7 @@ There is no eager-PyTorch implementation of the arithmetic here and no CPU path.
 import json
 import math
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -76,6 +77,11 @@ class WanSelfAttention(nn.Module):
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_owner_ref", None)      # weak link to the owning block: re-created by the block's __setstate__
+        return state
+
     def forward(self, x, seq_lens, grid_sizes, freqs):
         """model.py:127-156 for a standalone call: x [B, L, C] (already normalised + modulated)."""
         blk = _OwnerRef.get(self)
@@ -93,16 +99,20 @@ WAN_CROSSATTENTION_CLASSES = {"t2v_cross_attn": WanT2VCrossAttention}
 
 
 class _OwnerRef:
-    """Maps an attention sub-module to its owning block without creating a module cycle."""
-    _owners = {}
+    """Maps an attention sub-module to its owning block through a weak reference stored on the child (no module
+    cycle, nothing kept alive after `del model`; deepcopy / pickle re-create it in WanAttentionBlock.__setstate__)."""
 
-    @classmethod
-    def set(cls, child, owner):
-        cls._owners[id(child)] = owner
+    @staticmethod
+    def set(child, owner):
+        object.__setattr__(child, "_owner_ref", weakref.ref(owner))
 
-    @classmethod
-    def get(cls, child):
-        return cls._owners[id(child)]
+    @staticmethod
+    def get(child):
+        ref = getattr(child, "_owner_ref", None)
+        owner = ref() if ref is not None else None
+        if owner is None:
+            raise RuntimeError("attention module is not attached to a live WanAttentionBlock")
+        return owner
 
 
 class WanAttentionBlock(nn.Module):
@@ -124,6 +134,13 @@ class WanAttentionBlock(nn.Module):
         _OwnerRef.set(self.self_attn, self)
         _OwnerRef.set(self.cross_attn, self)
         self._packed = None
+
+    def __setstate__(self, state):
+        state = dict(state)
+        state["_packed"] = None            # packed weights are rebuilt lazily for the copy
+        super().__setstate__(state)
+        _OwnerRef.set(self.self_attn, self)
+        _OwnerRef.set(self.cross_attn, self)
 
     # -- engine plumbing -----------------------------------------------------------------------
     def _weights(self):
@@ -162,8 +179,7 @@ class WanAttentionBlock(nn.Module):
             cs = E.rope_cos_sin(freqs.cpu(), grid, L, 0, L, x.device)
             ws.h.copy_(x[i])
             E.mv.gemm(ws.h, bw.w_qkv, bw.b_qkv, ws.qkv, E.mv.MV_EPI_BF16)
-            E.mv.rmsnorm_rope(ws.qkv[:, 0:C], bw.g_q, cs, 128, bw.eps)
-            E.mv.rmsnorm_rope(ws.qkv[:, C:2 * C], bw.g_k, cs, 128, bw.eps)
+            E.mv.qkv_norm_rope(ws.qkv, bw.g_q, bw.g_k, cs, 128, bw.eps)
             E.self_attention_core(ws, L, int(seq_lens[i]), self.num_heads)
             y = torch.empty(L, C, dtype=torch.bfloat16, device=x.device)
             E.mv.gemm(ws.attn, bw.w_o, bw.b_o, y, E.mv.MV_EPI_BF16)
@@ -256,8 +272,23 @@ class WanModel(nn.Module):
         self.freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
                                 rope_params(1024, 2 * (d // 6))], dim=1)
         self._engine = None
+        self.keep_fp32_parameters()
         if init:
             self.init_weights()
+
+    def keep_fp32_parameters(self):
+        """The parameters the reference uses OUTSIDE bf16 autocast stay fp32 whatever `dtype` the model was created /
+        loaded with: time_embedding, time_projection and the head run inside `amp.autocast(dtype=float32)` regions
+        (model.py:340-343,541-545), the adaLN `modulation` tables are added in fp32 (:292-295), RMSNorm / norm3 gains
+        multiply fp32 values (:83-86,97-99).  Only the operands of the bf16-autocast Linears / the patch Conv3d may be
+        stored in bf16 (autocast rounds them to bf16 at every call anyway, biases included)."""
+        for m in (self.time_embedding, self.time_projection, self.head):
+            m.float()
+        for b in self.blocks:
+            b.modulation.data = b.modulation.data.float()
+            for n in (b.norm3, b.self_attn.norm_q, b.self_attn.norm_k, b.cross_attn.norm_q, b.cross_attn.norm_k):
+                n.float()
+        return self
 
     # -- engine ------------------------------------------------------------------------------------
     def engine(self):

@@ -210,6 +210,17 @@ class T5Encoder(nn.Module):
             self._engine = T5Engine(self)
         return self._engine
 
+    # the engine snapshots fp32 norm gains and the relative-position tables: any parameter change invalidates it
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._engine = None
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._engine = None
+        return r
+
     @staticmethod
     def _prefix_len(mask_row, L):
         if mask_row is None:

@@ -35,8 +35,14 @@ def synthetic_text_embedding(prompt, text_dim=4096, max_len=512, device="cpu"):
 class WanT2V:
 
     def __init__(self, config, checkpoint_dir, device_id=0, rank=0, t5_fsdp=False, dit_fsdp=False, use_usp=False,
-                 t5_cpu=False, model=None, vae=None):
+                 t5_cpu=False, model=None, vae=None, allow_random_init=False):
+        """Reference signature (text2video.py:31-41) + three extensions: `model` / `vae` inject already-built modules
+        (benchmarks, tests); `allow_random_init=True` lets MISSING checkpoint files fall back to random-init weights
+        and synthetic text embeddings — without it a missing file raises FileNotFoundError like the reference does."""
         self.device = torch.device("cuda:%d" % device_id)
+        self.allow_random_init = allow_random_init
+        if t5_cpu:
+            logging.info("t5_cpu=True: the umT5 encoder still runs on the GPU here (there is no CPU path)")
         self.config = config
         self.rank = rank
         self.t5_cpu = t5_cpu
@@ -56,16 +62,29 @@ class WanT2V:
             self.text_encoder = T5EncoderModel(text_len=config.text_len, dtype=config.t5_dtype, device=self.device,
                                                checkpoint_path=t5_pth, tokenizer_path=t5_tok)
         else:
-            logging.warning("no umT5 checkpoint/tokenizer under %r: prompts map to synthetic text embeddings", ckpt)
+            # generate() also accepts pre-computed embeddings (context=...), so a missing encoder only matters when a
+            # prompt has to be encoded: encode_prompt() raises then unless allow_random_init
+            logging.warning("no umT5 checkpoint/tokenizer under %r", ckpt)
             self.text_encoder = None
         vae_pth = os.path.join(ckpt, config.vae_checkpoint)
-        self.vae = vae if vae is not None else WanVAE(vae_pth=vae_pth if os.path.isfile(vae_pth) else None,
-                                                      device=self.device)
+        if vae is not None:
+            self.vae = vae
+        elif os.path.isfile(vae_pth):
+            self.vae = WanVAE(vae_pth=vae_pth, device=self.device)
+        elif allow_random_init:
+            logging.warning("no VAE checkpoint %r: random-init WanVAE", vae_pth)
+            self.vae = WanVAE(vae_pth=None, device=self.device)
+        else:
+            raise FileNotFoundError("WanVAE checkpoint %r not found (pass allow_random_init=True for a random-init "
+                                    "smoke run)" % vae_pth)
         if model is not None:
             self.model = model
         elif os.path.isfile(os.path.join(ckpt, "config.json")):
             logging.info("Creating WanModel from %s", ckpt)
             self.model = WanModel.from_pretrained(ckpt, device=self.device, dtype=torch.bfloat16)
+        elif not allow_random_init:
+            raise FileNotFoundError("no DiT checkpoint (config.json + *.safetensors) under %r (pass "
+                                    "allow_random_init=True for a random-init smoke run)" % ckpt)
         else:
             logging.warning("no DiT checkpoint under %r: using random-init weights of the configured architecture", ckpt)
             self.model = WanModel(model_type="t2v", patch_size=config.patch_size, text_len=config.text_len,
@@ -96,6 +115,9 @@ class WanT2V:
     def encode_prompt(self, prompt):
         if self.text_encoder is not None:                      # text2video.py:174-184 (always on the GPU here)
             return self.text_encoder([prompt], self.device)
+        if not self.allow_random_init:
+            raise FileNotFoundError("the umT5 checkpoint / tokenizer is missing: pass context= / context_null= "
+                                    "embeddings to generate(), or allow_random_init=True for synthetic ones")
         return [synthetic_text_embedding(prompt, 4096, self.config.text_len, self.device)]
 
     def denoise_step(self, scheduler, latent, t, context, context_null, seq_len, guide_scale):
@@ -104,6 +126,8 @@ class WanT2V:
         timestep = torch.stack([t])
         cond = self.model([latent], t=timestep, context=context, seq_len=seq_len)[0]
         uncond = self.model([latent], t=timestep, context=context_null, seq_len=seq_len)[0]
+        if hasattr(scheduler, "step_cfg"):      # UniPC: CFG + scheduler update fused into one kernel
+            return scheduler.step_cfg(cond, uncond, guide_scale, t, latent)[0]
         noise_pred = uncond + guide_scale * (cond - uncond)
         return scheduler.step(noise_pred.unsqueeze(0), t, latent.unsqueeze(0), return_dict=False)[0].squeeze(0)
 
@@ -119,6 +143,8 @@ class WanT2V:
     def generate(self, input_prompt, size=(1280, 720), frame_num=81, shift=5.0, sample_solver="unipc",
                  sampling_steps=50, guide_scale=5.0, n_prompt="", seed=-1, offload_model=True, context=None,
                  context_null=None, decode=True):
+        if offload_model:
+            logging.debug("offload_model=True is ignored: the bf16 DiT (28.6 GB) and the VAE stay resident on the B200")
         target_shape, seq_len = self.latent_geometry(size, frame_num)
         if n_prompt == "":
             n_prompt = self.sample_neg_prompt

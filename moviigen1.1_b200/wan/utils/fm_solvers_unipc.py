@@ -129,8 +129,83 @@ class FlowUniPCMultistepScheduler:
         idx = [k for k, v in enumerate(self._timesteps_host) if v == t]
         self._step_index = idx[1] if len(idx) > 1 else idx[0]                 # :629-640
 
+    # -- fused device path: CFG + convert_model_output + UniC + UniP in ONE sm_100a kernel (mv_unipc_cfg_step) -------
+    def _predict_coefs(self, order):
+        i = self._step_index
+        prev = [i - k for k in range(1, order)]
+        ratio, alpha_t, h_phi_1, B_h, rks, R, b = self._coeffs(i + 1, i, prev, order)
+        rhos = []
+        if order == 2:
+            rhos = [0.5]
+        elif order > 2:
+            rhos = torch.linalg.solve(R[:-1, :-1], b[:-1]).tolist()
+        return (float(ratio), float(alpha_t * h_phi_1), float(alpha_t * B_h), [float(r) for r in rks[:order - 1]],
+                [float(r) for r in rhos[:order - 1]])
+
+    def _correct_coefs(self, order):
+        i = self._step_index
+        prev = [i - (k + 1) for k in range(1, order)]
+        ratio, alpha_t, h_phi_1, B_h, rks, R, b = self._coeffs(i, i - 1, prev, order)
+        rhos = [0.5] if order == 1 else torch.linalg.solve(R, b).tolist()
+        return (float(ratio), float(alpha_t * h_phi_1), float(alpha_t * B_h), float(rhos[-1]),
+                [float(r) for r in rks[:order - 1]], [float(r) for r in rhos[:order - 1]])
+
+    def step_cfg(self, cond, uncond, guide_scale, timestep, sample):
+        """The latent-sized arithmetic of one sampling step (text2video.py:245-254 + step(), :656-742) as ONE kernel:
+        noise = uncond + guide_scale*(cond - uncond), x0, corrector, predictor.  CUDA fp32 tensors only; the host
+        computes the scalar coefficients exactly as step() does.  Returns (prev_sample, x0)."""
+        import movii_b200 as mv
+        if self.num_inference_steps is None:
+            raise ValueError("run set_timesteps first")
+        if self.solver_order > 3:
+            raise NotImplementedError("mv_unipc_cfg_step supports solver_order <= 3")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        i = self._step_index
+        shape = sample.shape
+        f = lambda t: None if t is None else t.reshape(-1)  # noqa: E731
+        cond, uncond, sample = (t.contiguous() for t in (cond, uncond, sample))
+        use_corrector = i > 0 and (i - 1) not in self.disable_corrector and self.last_sample is not None
+        coef = [0.0] * mv.UNIPC_NCOEF
+        coef[0], coef[1], coef[2] = float(guide_scale), float(self.sigmas[i]), 1.0 if use_corrector else 0.0
+        if use_corrector:
+            co = self.this_order
+            ratio, ca, cb, rho_last, rks, rhos = self._correct_coefs(co)
+            coef[3:8] = [float(co), ratio, ca, cb, rho_last]
+            for k, (rk, rho) in enumerate(zip(rks, rhos)):
+                coef[8 + k], coef[10 + k] = rk, rho
+        order = min(self.solver_order, len(self._timesteps_host) - i) if self.lower_order_final else self.solver_order
+        this_order = min(order, self.lower_order_nums + 1)
+        ratio, pa, pb, rks, rhos = self._predict_coefs(this_order)
+        coef[12:16] = [float(this_order), ratio, pa, pb]
+        for k, (rk, rho) in enumerate(zip(rks, rhos)):
+            coef[16 + k], coef[18 + k] = rk, rho
+        hist = [self.model_outputs[-1 - k] if k < self.solver_order else None for k in range(3)]
+        x0 = torch.empty_like(sample)          # fresh tensors, like the reference (callers may keep them)
+        s_out = torch.empty_like(sample)
+        prev = torch.empty_like(sample)
+        mv.unipc_cfg_step(f(cond), f(uncond), f(sample), f(self.last_sample), [f(h) for h in hist], coef, f(x0), f(s_out),
+                          f(prev))
+        for k in range(self.solver_order - 1):
+            self.model_outputs[k] = self.model_outputs[k + 1]
+            self.timestep_list[k] = self.timestep_list[k + 1]
+        self.model_outputs[-1] = x0.view(shape)
+        self.timestep_list[-1] = timestep
+        self.this_order = this_order
+        self.last_sample = s_out.view(shape)
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        return prev.view(shape), self.model_outputs[-1]
+
     def step(self, model_output, timestep, sample, return_dict=True, generator=None):
-        """:656-742.  Returns (prev_sample, x0_pred) when return_dict=False."""
+        """:656-742.  Returns (prev_sample, x0_pred) when return_dict=False.  CUDA fp32 tensors run through the fused
+        kernel (guide 0 makes the CFG stage the identity: m + 0*(m - m)); CPU tensors (host-side tests against the
+        reference trajectories) through the equivalent torch expressions below."""
+        if model_output.is_cuda and model_output.dtype == torch.float32 and sample.dtype == torch.float32 \
+                and self.solver_order <= 3:
+            prev, x0 = self.step_cfg(model_output, model_output, 0.0, timestep, sample)
+            return (prev, x0) if not return_dict else {"prev_sample": prev}
         if self.num_inference_steps is None:
             raise ValueError("run set_timesteps first")
         if self._step_index is None:

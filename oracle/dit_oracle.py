@@ -107,7 +107,7 @@ def linear(x, w, b, rb):
     """nn.Linear; with rb = bf16_rt: autocast semantics (bf16 inputs/weights, fp32 accumulate, bf16 out)."""
     y = rb(x.float()) @ rb(w.float()).t()
     if b is not None:
-        y = y + b.float()
+        y = y + rb(b.float())      # autocast casts EVERY tensor argument of linear to bf16, the bias included
     return rb(y)
 
 
@@ -117,9 +117,19 @@ def attention(q, k, v, rb, scale=None):
     d = q.shape[-1]
     scale = d ** -0.5 if scale is None else scale
     qh, kh, vh = (rb(t.float()).transpose(0, 1) for t in (q, k, v))  # [n, L, d]
-    s = torch.matmul(qh, kh.transpose(1, 2)) * scale
-    p = torch.softmax(s, dim=-1)
-    return rb(torch.matmul(p, vh).transpose(0, 1).contiguous())
+    if qh.shape[1] * kh.shape[1] * qh.shape[0] <= (1 << 28):
+        s = torch.matmul(qh, kh.transpose(1, 2)) * scale
+        p = torch.softmax(s, dim=-1)
+        return rb(torch.matmul(p, vh).transpose(0, 1).contiguous())
+    # long sequences (full-size parity runs of this oracle on a GPU): same arithmetic, one head and <= 4096 query rows
+    # at a time so that the score block stays small; every row's softmax is still exact over all keys
+    out = torch.empty(qh.shape[0], qh.shape[1], vh.shape[2], dtype=torch.float32, device=q.device)
+    for h in range(qh.shape[0]):
+        kt = kh[h].t().contiguous()
+        for r0 in range(0, qh.shape[1], 4096):
+            p = torch.softmax(torch.matmul(qh[h, r0:r0 + 4096], kt) * scale, dim=-1)
+            out[h, r0:r0 + 4096] = torch.matmul(p, vh[h])
+    return rb(out.transpose(0, 1).contiguous())
 
 
 def gelu_tanh(x):

@@ -222,6 +222,52 @@ def test_rmsnorm_rope(mv, M, C, hd, rope):
     assert torch.equal(xd[:, :8].cpu(), x[:, :8]) and torch.equal(xd[:, 8 + C:].cpu(), x[:, 8 + C:])
 
 
+@pytest.mark.parametrize("M,C,hd,P", [(9, 256, 128, 0), (40, 5120, 128, 0), (33, 5120, 128, 8), (21, 1024, 128, 4),
+                                      (6, 128, 32, 2), (5, 7680, 128, 0)])
+def test_qkv_norm_rope_fused(mv, M, C, hd, P):
+    """q and k RMSNorm + RoPE (and, with P > 0, the Ulysses head scatter of q, k, v) of a fused QKV row in ONE launch ==
+    the per-tensor oracle; V is copied bit-exactly; padding columns of the buffer are untouched."""
+    g = torch.Generator().manual_seed(M + C + P)
+    ld = 3 * C + 16
+    x = (torch.randn(M, ld, generator=g) * 2).bfloat16()
+    gq, gk = 1 + 0.2 * torch.randn(C, generator=g), 1 + 0.2 * torch.randn(C, generator=g)
+    ang = O.rope_table((M, 1, 1), hd, M)
+    ref = {}
+    for name, c0, wt in (("q", 0, gq), ("k", C, gk)):
+        y = O.rms_norm(x[:, c0:c0 + C], wt, 1e-6, O.bf16_rt)
+        ref[name] = O.bf16_rt(O.rope_apply(y.view(M, C // hd, hd), ang).reshape(M, C))
+    ref["v"] = x[:, 2 * C:3 * C].float()
+    cs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(DEV)
+    xd = x.to(DEV)
+    qkv = xd[:, :3 * C]
+    if P == 0:
+        mv.qkv_norm_rope(qkv, gq.to(DEV), gk.to(DEV), cs, hd, 1e-6)
+        assert rel_l2(xd[:, 0:C].float(), ref["q"]) <= 3e-3 and rel_l2(xd[:, C:2 * C].float(), ref["k"]) <= 3e-3
+        assert torch.equal(xd[:, 2 * C:].cpu(), x[:, 2 * C:])              # v and the padding are untouched
+    else:
+        slot = 1                                                        # write into slab `slot` of [P slots, M, C/P] buffers
+        bufs = {n: torch.full((P, P, M, C // P), float("nan"), dtype=torch.bfloat16, device=DEV) for n in "qkv"}
+        tabs = tuple(mv.ptr_table([bufs[n][d].data_ptr() for d in range(P)]) for n in "qkv")
+        mv.qkv_norm_rope(qkv, gq.to(DEV), gk.to(DEV), cs, hd, 1e-6, dst=tabs, n_dst=P, src_slot=slot)
+        assert torch.equal(xd.cpu(), x)                                  # the source rows are not modified
+        for n in "qkv":
+            got = bufs[n][:, slot].permute(1, 0, 2).reshape(M, C).float()   # [dst][row][C/P] -> [row][C]
+            if n == "v":
+                assert torch.equal(got.cpu(), ref["v"])
+            else:
+                assert rel_l2(got, ref[n]) <= 3e-3, n
+            other = torch.cat([bufs[n][:, :slot], bufs[n][:, slot + 1:]], dim=1)
+            assert torch.isnan(other.float()).all()                          # nothing outside the addressed slab
+
+
+def test_modulation_table(mv):
+    g = torch.Generator().manual_seed(4)
+    mods, e0 = torch.randn(5, 6, 384, generator=g), torch.randn(6 * 384, generator=g)
+    out = torch.empty(5, 6, 384, device=DEV)
+    mv.modulation_table(mods.to(DEV), e0.to(DEV), out)
+    assert torch.equal(out.cpu(), mods + e0.view(1, 6, 384))
+
+
 def test_patchify(mv):
     g = torch.Generator().manual_seed(3)
     lat = torch.randn(16, 3, 8, 12, generator=g)

@@ -48,6 +48,22 @@ def main():
         rel = ((ysp - y1).double().norm() / y1.double().norm()).item()
         rels[mode] = rel
         ok = ok and rel <= 2e-3 and bool(torch.isfinite(ysp).all())
+    # the per-module seam (text2video.py:97-99 binds usp_attn_forward onto every block's self_attn): standalone call on
+    # this rank's token shard vs the single-GPU WanSelfAttention.forward on the full sequence
+    from wan.distributed.xdit_context_parallel import usp_attn_forward
+    from wan.distributed.ulysses import token_range
+    blk = m.blocks[0]
+    h = torch.randn(1, seq_len, cfg["dim"], generator=g).to(dev).bfloat16()
+    grid_sizes, seq_lens = torch.tensor([[3, 8, 16]]), torch.tensor([seq_len])
+    a1 = type(blk.self_attn).forward(blk.self_attn, h, seq_lens, grid_sizes, m.freqs)
+    start, rows = token_range(seq_len, world, rank)
+    for mode in ("nccl", "p2p"):
+        get_sp_group().ulysses.mode = mode
+        asp = usp_attn_forward(blk.self_attn, h[:, start:start + rows].contiguous(), seq_lens, grid_sizes, m.freqs)
+        ref = a1[:, start:start + rows].float()
+        rel_a = ((asp.float() - ref).double().norm() / ref.double().norm()).item()
+        rels["attn_" + mode] = rel_a
+        ok = ok and rel_a <= 2e-3 and bool(torch.isfinite(asp.float()).all())
     rel = max(rels.values())
     if rank == 0:
         print("per-mode rel-L2:", rels, flush=True)
