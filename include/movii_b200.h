@@ -54,6 +54,11 @@ int mv_device_check(void);
 int mv_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
                  int64_t ldo, const float* gate, int M, int N, int K, int epilogue, mv_stream_t stream);
 
+/* mv_gemm_bf16 with IEEE fp16 operands and fp16 (MV_EPI_BF16 / _GELU slots) or fp32 outputs: the two contractions of the
+ * WanVAE AttentionBlock (vae.py:246-257), whose activations are fp16 here. */
+int mv_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out, int64_t ldo,
+                const float* gate, int M, int N, int K, int epilogue, mv_stream_t stream);
+
 /* Same contraction with A stored as K/a_kblock slabs: A[m, j*a_kblock + c] = A_base[j*a_block_stride + m*lda + c].
  * This is the layout the Ulysses attention-output all-to-all delivers ([src rank][local token][local heads*128],
  * xdit_context_parallel.py:185-197), so the o projection consumes it without a transpose pass.
@@ -180,7 +185,8 @@ int mv_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t 
                              int Lk, int H, float softmax_scale, mv_stream_t stream);
 
 /* ---- WanVAE decoder (wan/modules/vae.py) ------------------------------------------------------- */
-/* Activations are channels-last bf16 [T, H, W, C]; weights are packed per conv as bf16 [Cout_pad][tap][Cin]. */
+/* Activations are channels-last FP16 [T, H, W, C]; weights are packed per conv as fp16 [Cout_pad][tap][Cin]; fp32
+ * accumulation.  (fp16 keeps the 10 mantissa bits of the TF32 convolutions the reference runs with autocast disabled.) */
 
 /* Stride-1 "same" convolution as an implicit GEMM on tcgen05 (csrc/vae_conv_sm100.cu):
  *   out[t,h,w,:] = bias + sum_i in[t+dt_i, h+dh_i, w+dw_i, :] . W[:, i, :]^T (+ res[t,h,w,:])
@@ -189,35 +195,39 @@ int mv_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t 
  * voxel (t,h,w) is o_base + t*os_t + h*os_h + w*os_w, which expresses the sub-pixel (nearest-2x + Conv2d,
  * vae.py:74-79) and frame-interleave (time_conv, vae.py:128-137) stores; output channel blocks >= nsplit are
  * written to channel (n - nsplit) at offset + nsplit_off (nsplit = 0 disables).
- * out_mode 0: bf16 channels-last (+ optional bf16 residual with the same addressing);
- * out_mode 1: fp32 channel-first [cout_real, T, H, W] clamped to [-1, 1] (decoder head, vae.py:465-471,660-661). */
+ * Temporal chunking (the reference's feature cache, vae.py:28-36,205-217): the input holds in_T = t_off + out_T frames,
+ * the first t_off being the cached tail of the previous chunk; output frame t reads input frames t + t_off + dt.
+ * out_mode 0: fp16 channels-last (+ optional fp16 residual with the same addressing);
+ * out_mode 1: fp32 channel-first video clamped to [-1, 1] (decoder head, vae.py:465-471,660-661): element
+ * out[c*os_t + o_base + (t*H + h)*W + w] (os_t = channel stride = T_total*H*W, o_base = first frame * H*W; os_t = 0:
+ * a dense [cout_real, out_T, H, W] tensor). */
 int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed, const float* bias,
                 const void* res_cl, void* out, int out_mode, int out_T, int out_H, int out_W, int Cout, int cout_real,
                 int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t, int64_t os_h, int64_t os_w,
-                int nsplit, int64_t nsplit_off, mv_stream_t stream);
+                int nsplit, int64_t nsplit_off, int t_off, mv_stream_t stream);
 
-/* mv_vae_conv (bf16 channels-last output) with the CONSUMER's RMS_norm + SiLU fused into the epilogue
+/* mv_vae_conv (fp16 channels-last output) with the CONSUMER's RMS_norm + SiLU fused into the epilogue
  * (vae.py:194-199: every conv of a ResidualBlock is fed silu(rms_norm(.))): norm_out[voxel,:] =
  * silu(rms_norm(out[voxel,:]) * gamma) with the same addressing as out; out may be NULL when only the normalised
  * tensor is consumed.  Requires Cout <= 256 (whole channel row in one tile). */
 int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed, const float* bias,
                       const void* res_cl, void* out, int out_T, int out_H, int out_W, int Cout, int ntaps,
                       const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t, int64_t os_h, int64_t os_w,
-                      const float* norm_gamma, void* norm_out, mv_stream_t stream);
+                      const float* norm_gamma, void* norm_out, int t_off, mv_stream_t stream);
 
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per voxel over channels (RMS_norm + nn.SiLU,
- * vae.py:39-54,194-199); channels-last bf16, in place allowed. */
+ * vae.py:39-54,194-199); channels-last fp16, in place allowed. */
 int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,
                         mv_stream_t stream);
 
 /* x_cl[v, o] = sum_c W2[o,c] * (z[c, v] * std[c] + mean[c]) + b2[o]: latent de-normalisation + conv2 (1x1x1) +
- * fp32 channel-first -> bf16 channels-last (vae.py:547-553,629-639). */
+ * fp32 channel-first -> fp16 channels-last (vae.py:547-553,629-639). */
 int mv_vae_latent_in(const float* z, const float* W2, const float* b2, const float* mean, const float* stdv,
                      void* out_cl, int Z, int64_t nvox, mv_stream_t stream);
 
-/* P_bf16[m, :N] = softmax(S[m, :N] * scale) (fp32 in): the softmax of the VAE's single-head attention between the
+/* P_f16[m, :N] = softmax(S[m, :N] * scale) (fp32 in, fp16 out): the softmax of the VAE's single-head attention between the
  * two tcgen05 GEMMs (vae.py:246-257). */
-int mv_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int M, int N, float scale,
+int mv_softmax_rows(const float* S, int64_t lds, void* P_f16, int64_t ldp, int M, int N, float scale,
                     mv_stream_t stream);
 
 /* Diagnostics only: mv_attention_fwd (128-key-step kernel) that also writes clock64 stamps of CTA (0, head 0) to

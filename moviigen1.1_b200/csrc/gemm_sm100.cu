@@ -45,6 +45,7 @@ struct GemmParams {
   int M, N, K;
   int num_m, num_n, num_tiles, num_kb;
   int a_kblock;  // > 0: A is split along K into blocks of a_kblock columns (3-D tensor map {k, m, block})
+  int f16;         // 1: operands (and 16-bit outputs) are IEEE fp16 instead of bf16 (mv_gemm_f16: WanVAE attention)
   int stream_out;  // 1 (MV_GEMM_STREAM=1): ld/st.global.cs (evict-first) for the output and the fp32 residual, so that
                    // this one-touch traffic does not push the re-used A / W tiles out of L2 (ncu: 4.4 GB DRAM reads
                    // for 2.4 GB algorithmic on the 75600 x 5120 x 5120 residual GEMM).  Measured neutral: off.
@@ -131,7 +132,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    const uint32_t idesc = p.f16 ? make_idesc_f16(BM, BN, 0, 0) : make_idesc_bf16(BM, BN, 0, 0);
     const uint64_t adesc0 = make_desc_kmajor_sw128(smem_u32(sA));
     const uint64_t bdesc0 = make_desc_kmajor_sw128(smem_u32(sB));
     int stage = 0;
@@ -240,7 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                           __uint_as_float(a.w) + b4[3]};
             if constexpr (EPI != MV_EPI_F32) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) v[i] = bf16_round(v[i]);
+              for (int i = 0; i < 4; ++i) v[i] = p.f16 ? f16_round(v[i]) : bf16_round(v[i]);
             }
             if constexpr (EPI == MV_EPI_BF16_GELU) {
 #pragma unroll
@@ -249,11 +250,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (EPI == MV_EPI_BF16 || EPI == MV_EPI_BF16_GELU) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo + col;
               if (col_full) {
-                const uint2 w2 = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                const uint2 w2 = p.f16 ? make_uint2(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]))
+                                       : make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
                 if (p.stream_out) __stcs(reinterpret_cast<uint2*>(o), w2);
                 else *reinterpret_cast<uint2*>(o) = w2;
               } else {
-                for (int i = 0; i < 4 && col + i < p.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
+                for (int i = 0; i < 4 && col + i < p.N; ++i) {
+                  if (p.f16) reinterpret_cast<__half*>(o)[i] = __float2half_rn(f16_sat(v[i]));
+                  else o[i] = __float2bfloat16_rn(v[i]);
+                }
               }
             } else {
               float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(row) * p.ldo + col;
@@ -324,7 +329,7 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
 
 static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_kblock, const void* W, int64_t ldw,
                      const float* bias, void* out, int64_t ldo, const float* gate, int M, int N, int K, int epilogue,
-                     mv_stream_t stream) {
+                     mv_stream_t stream, int f16 = 0) {
   using namespace mv;
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
@@ -385,6 +390,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
   p.num_tiles = p.num_m * p.num_n;
   p.num_kb = (K + BK - 1) / BK;
   p.a_kblock = a_kblock;
+  p.f16 = f16;
   {
     static int stream = -1;   // MV_GEMM_STREAM=1 turns the evict-first accesses on; measured neutral (+-3 %), default off
     if (stream < 0) {
@@ -407,4 +413,9 @@ extern "C" int mv_gemm_bf16_ksplit(const void* A, int64_t lda, int64_t a_block_s
                                    int64_t ldw, const float* bias, void* out, int64_t ldo, const float* gate, int M,
                                    int N, int K, int epilogue, mv_stream_t stream) {
   return gemm_impl(A, lda, a_block_stride, a_kblock, W, ldw, bias, out, ldo, gate, M, N, K, epilogue, stream);
+}
+
+extern "C" int mv_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                           int64_t ldo, const float* gate, int M, int N, int K, int epilogue, mv_stream_t stream) {
+  return gemm_impl(A, lda, 0, 0, W, ldw, bias, out, ldo, gate, M, N, K, epilogue, stream, 1);
 }

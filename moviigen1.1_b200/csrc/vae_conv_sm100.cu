@@ -1,4 +1,6 @@
-// WanVAE decoder convolutions as an implicit GEMM on tcgen05 (channels-last bf16 activations).
+// WanVAE decoder convolutions as an implicit GEMM on tcgen05 (channels-last FP16 activations and weights: 10 mantissa
+// bits like the TF32 convolutions the reference runs, fp32 accumulation; max-abs 4e-3 vs the fp32 reference where bf16
+// storage measured 3e-2 — tests/test_vae_gpu.py).
 //
 //   out[t,h,w,:] = bias + sum_taps  in[t+dt, h+dh, w+dw, :] . Wtap^T        (+ residual)
 //
@@ -30,24 +32,26 @@ constexpr uint32_t kConvSmem = kConvRingBytes + 1024 + 512;
 
 struct ConvParams {
   const float* bias;            // [Cout] or null
-  const __nv_bfloat16* res;     // residual, same addressing as out (bf16 channels-last) or null
+  const __half* res;     // residual, same addressing as out (fp16 channels-last) or null
   void* out;
   // output addressing (elements): off = base + t*os_t + h*os_h + w*os_w (+ parity remap) + channel
   int64_t o_base, os_t, os_h, os_w;
   int nsplit;                   // > 0: output channel block n0 >= nsplit goes to (n0 - nsplit) with + nsplit_off
   int64_t nsplit_off;
-  int T, H, W;                  // output grid (== input grid: stride-1 "same" convolutions)
+  int T, H, W;                  // output grid (stride-1 "same" convolutions: input H, W equal; input T = t_off + T)
+  int t_off;                    // output frame t reads input frames t + t_off + dt: the first t_off input frames are the
+                                // cached tail of the previous temporal chunk (CausalConv3d feature cache, vae.py:28-36,205-217)
   int Cin, Cout;
   int BN;                       // N tile (multiple of 16, <= 256)
   int ntaps;
   int8_t dt[kConvMaxTaps], dh[kConvMaxTaps], dw[kConvMaxTaps];
   int num_n, tiles_h, tiles_w, num_tiles, kblocks_per_tap;
-  int out_mode;                 // 0: bf16 channels-last; 1: fp32 channel-first video [Cout_real,T,H,W] clamped to [-1,1]
+  int out_mode;                 // 0: fp16 channels-last; 1: fp32 channel-first video [Cout_real,T,H,W] clamped to [-1,1]
   int cout_real;                // out_mode 1: number of real output channels (3)
   int stages;                   // ring depth (<= kConvMaxStages)
   uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes (kps blocks each)
   const float* norm_gamma;      // fused RMS_norm + SiLU of the output row (needs BN == Cout): gamma [Cout] or null
-  __nv_bfloat16* norm_out;      // where silu(rms_norm(out)) goes (same addressing as out); `out` may then be null
+  __half* norm_out;      // where silu(rms_norm(out)) goes (same addressing as out); `out` may then be null
   int kps;                      // k-blocks per ring slot (3 for Cin = 96: one whole tap per slot, 6 MMAs per barrier trip)
   uint32_t a_block_bytes, b_block_bytes;
 };
@@ -127,7 +131,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int tap = (kb + i) / p.kblocks_per_tap;
             const int cb = (kb + i) - tap * p.kblocks_per_tap;
             tma_load_4d(sA + stage * kConvABytesMax + i * p.a_block_bytes, &tmA, &full[stage], cb * BK,
-                        w0 + p.dw[tap], h0 + p.dh[tap], t + p.dt[tap]);
+                        w0 + p.dw[tap], h0 + p.dh[tap], t + p.t_off + p.dt[tap]);
             tma_load_2d(sB + stage * kConvBBytesMax + i * p.b_block_bytes, &tmB, &full[stage],
                         tap * p.Cin + cb * BK, n_blk * p.BN);
           }
@@ -140,7 +144,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(kConvBM, static_cast<uint32_t>(p.BN), 0, 0);
+    const uint32_t idesc = make_idesc_f16(kConvBM, static_cast<uint32_t>(p.BN), 0, 0);
     const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, Cfg::kSBO, Cfg::kLayout);
     const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, Cfg::kSBO, Cfg::kLayout);
     int stage = 0;
@@ -225,25 +229,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    f[8 * i + 2 * k] += bf16_lo(u[k]);
-                    f[8 * i + 2 * k + 1] += bf16_hi(u[k]);
+                    f[8 * i + 2 * k] += f16_lo(u[k]);
+                    f[8 * i + 2 * k + 1] += f16_hi(u[k]);
                   }
                 }
               }
             }
-            __nv_bfloat16* dst = nullptr;
+            __half* dst = nullptr;
             if (pass == 0) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                f[i] = bf16_round(f[i]);      // statistics of the value as it is stored
+                f[i] = f16_round(f[i]);      // statistics of the value as it is stored
                 ss += f[i] * f[i];
               }
-              if (p.out != nullptr) dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c;
+              if (p.out != nullptr) dst = reinterpret_cast<__half*>(p.out) + off + c;
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float gmm = i < ncols ? __ldg(p.norm_gamma + c + i) : 0.f;
-                const float y = bf16_round(f[i]) * inv * gmm;
+                const float y = f16_round(f[i]) * inv * gmm;
                 f[i] = y / (1.f + __expf(-y));
               }
               dst = p.norm_out + off + c;
@@ -254,10 +258,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int i = 0; i < 4; ++i) {
                 if (8 * i < ncols) {
                   uint4 q;
-                  q.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-                  q.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-                  q.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-                  q.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                  q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
+                  q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
+                  q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
+                  q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
                   o4[i] = q;
                 }
               }
@@ -278,7 +282,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               float b = (p.bias != nullptr && i < ncols && n0 + c + i < p.Cout) ? __ldg(p.bias + n0 + c + i) : 0.f;
               f[i] = __uint_as_float(v[i]) + b;
             }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + nb + c;
+            __half* o = reinterpret_cast<__half*>(p.out) + off + nb + c;
             if (p.res != nullptr) {
               const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + nb + c);
 #pragma unroll
@@ -288,8 +292,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    f[8 * i + 2 * k] += bf16_lo(u[k]);
-                    f[8 * i + 2 * k + 1] += bf16_hi(u[k]);
+                    f[8 * i + 2 * k] += f16_lo(u[k]);
+                    f[8 * i + 2 * k + 1] += f16_hi(u[k]);
                   }
                 }
               }
@@ -299,18 +303,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int i = 0; i < 4; ++i) {
               if (8 * i < ncols) {
                 uint4 q;
-                q.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-                q.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-                q.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-                q.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
+                q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
+                q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
+                q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
                 o4[i] = q;
               }
             }
           } else {
             // head conv: fp32 channel-first video, clamp(-1, 1)                       vae.py:660-661
             float* o = reinterpret_cast<float*>(p.out);
-            const int64_t plane = static_cast<int64_t>(p.T) * p.H * p.W;
-            const int64_t pos = (static_cast<int64_t>(t) * p.H + h) * p.W + w;
+            const int64_t plane = p.os_t > 0 ? p.os_t : static_cast<int64_t>(p.T) * p.H * p.W;   // channel stride
+            const int64_t pos = p.o_base + (static_cast<int64_t>(t) * p.H + h) * p.W + w;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if (c == 0 && i < p.cout_real) {
@@ -340,7 +344,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // --------------------------------------------------------------------------------------------
-// RMS_norm over channels + SiLU, channels-last bf16 -> bf16 (in place allowed).   vae.py:39-54 + nn.SiLU
+// RMS_norm over channels + SiLU, channels-last fp16 -> fp16 (in place allowed).   vae.py:39-54 + nn.SiLU
 // y = silu( x / max(||x||_2, 1e-12) * sqrt(C) * gamma (+ beta) );  one warp per voxel, C <= 512, C % 8 == 0.
 // silu == 0 skips the activation (AttentionBlock.norm, vae.py:233,246).
 // --------------------------------------------------------------------------------------------
@@ -348,7 +352,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // flight; two voxels per group are processed per iteration for memory-level parallelism.
 template <int G, int VPL>  // VPL = uint4 vectors per lane (C <= G * VPL * 8)
 __global__ void __launch_bounds__(256)
-rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+rmsnorm_silu_cl_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                        int64_t nvox, int C, int silu) {
   constexpr int kUnroll = 2;
   const int lane = threadIdx.x & 31;
@@ -388,7 +392,7 @@ rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
         const uint32_t w[4] = {a[u][j].x, a[u][j].y, a[u][j].z, a[u][j].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float lo = bf16_lo(w[k]), hi = bf16_hi(w[k]);
+          const float lo = f16_lo(w[k]), hi = f16_hi(w[k]);
           ss[u] += lo * lo + hi * hi;
         }
       }
@@ -409,13 +413,13 @@ rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
           uint32_t w[4] = {a[u][j].x, a[u][j].y, a[u][j].z, a[u][j].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            float lo = bf16_lo(w[k]) * inv * g[j][2 * k];
-            float hi = bf16_hi(w[k]) * inv * g[j][2 * k + 1];
+            float lo = f16_lo(w[k]) * inv * g[j][2 * k];
+            float hi = f16_hi(w[k]) * inv * g[j][2 * k + 1];
             if (silu) {
               lo = lo / (1.f + __expf(-lo));
               hi = hi / (1.f + __expf(-hi));
             }
-            w[k] = pack_bf16(lo, hi);
+            w[k] = pack_f16(lo, hi);
           }
           yr[idx] = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -425,12 +429,12 @@ rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
 }
 
 // --------------------------------------------------------------------------------------------
-// Latent de-normalisation + conv2 (1x1x1, 16 -> 16) + layout change to channels-last bf16.
+// Latent de-normalisation + conv2 (1x1x1, 16 -> 16) + layout change to channels-last fp16.
 // x[t,h,w,o] = sum_c W2[o,c] * (z[c,t,h,w] * std[c] + mean[c]) + b2[o]                vae.py:547-553
 // --------------------------------------------------------------------------------------------
 __global__ void vae_latent_in_kernel(const float* __restrict__ z, const float* __restrict__ W2, const float* __restrict__ b2,
                                      const float* __restrict__ mean, const float* __restrict__ stdv,
-                                     __nv_bfloat16* __restrict__ out, int Z, int64_t nvox) {
+                                     __half* __restrict__ out, int Z, int64_t nvox) {
   __shared__ float sw[32 * 32 + 96];
   float* sb = sw + Z * Z;
   float* sm = sb + Z;
@@ -449,17 +453,17 @@ __global__ void vae_latent_in_kernel(const float* __restrict__ z, const float* _
     for (int o = 0; o < Z; ++o) {
       float acc = sb[o];
       for (int c = 0; c < Z; ++c) acc = fmaf(sw[o * Z + c], zin[c], acc);
-      out[v * Z + o] = __float2bfloat16_rn(acc);
+      out[v * Z + o] = __float2half_rn(f16_sat(acc));
     }
   }
 }
 
 // --------------------------------------------------------------------------------------------
-// Row softmax for the VAE's single-head attention: P = softmax(S * scale), S fp32 [M, N] -> P bf16 [M, ldp].
+// Row softmax for the VAE's single-head attention: P = softmax(S * scale), S fp32 [M, N] -> P fp16 [M, ldp].
 // One CTA per row.                                                                 vae.py:246-257
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ S, int64_t lds, __nv_bfloat16* __restrict__ P, int64_t ldp, int N,
+softmax_rows_kernel(const float* __restrict__ S, int64_t lds, __half* __restrict__ P, int64_t ldp, int N,
                     float scale) {
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
@@ -482,8 +486,8 @@ softmax_rows_kernel(const float* __restrict__ S, int64_t lds, __nv_bfloat16* __r
   sum = 0.f;
   for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
   const float inv = 1.f / sum;
-  __nv_bfloat16* pr = P + row * ldp;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) pr[i] = __float2bfloat16_rn(__expf((s[i] - mx) * scale) * inv);
+  __half* pr = P + row * ldp;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) pr[i] = __float2half_rn(__expf((s[i] - mx) * scale) * inv);
 }
 
 template <int BK>
@@ -508,13 +512,16 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
                          const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
                          int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
                          int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
-                         const float* norm_gamma, void* norm_out, mv_stream_t stream) {
+                         const float* norm_gamma, void* norm_out, int t_off, mv_stream_t stream) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(ntaps >= 1 && ntaps <= kConvMaxTaps, "mv_vae_conv: ntaps=%d out of range", ntaps);
   MV_REQUIRE(Cin % 16 == 0 && Cin >= 16, "mv_vae_conv: Cin=%d must be a multiple of 16", Cin);
   MV_REQUIRE(Cout % 16 == 0, "mv_vae_conv: (padded) Cout=%d must be a multiple of 16", Cout);
   MV_REQUIRE(out_T > 0 && out_H > 0 && out_W > 0, "mv_vae_conv: empty output grid");
+  MV_REQUIRE(t_off >= 0 && in_T == out_T + t_off && in_H == out_H && in_W == out_W,
+             "mv_vae_conv: input grid %dx%dx%d does not match output %dx%dx%d + %d cached frames", in_T, in_H, in_W, out_T,
+             out_H, out_W, t_off);
   int BK = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
   int BN;
   if (Cout <= 256) BN = Cout;
@@ -536,6 +543,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
     uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)Cin * in_W * 2, (uint64_t)Cin * in_W * in_H * 2};
     uint32_t box[4] = {(uint32_t)BK, kConvTW, kConvTH, 1};
+    // (a 16-bit tensor map only moves bytes: the bf16 encoder serves fp16 data unchanged)
     rc = make_tmap_bf16_sw(&tmA, in_cl, 4, dims, str, box, BK * 2);
     if (rc != MV_OK) return rc;
   }
@@ -548,7 +556,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   }
   ConvParams p;
   p.bias = bias;
-  p.res = reinterpret_cast<const __nv_bfloat16*>(res_cl);
+  p.res = reinterpret_cast<const __half*>(res_cl);
   p.out = out;
   p.o_base = o_base;
   p.os_t = os_t;
@@ -557,6 +565,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   p.nsplit = nsplit;
   p.nsplit_off = nsplit_off;
   p.T = out_T;
+  p.t_off = t_off;
   p.H = out_H;
   p.W = out_W;
   p.Cin = Cin;
@@ -578,7 +587,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   p.out_mode = out_mode;
   p.cout_real = cout_real;
   p.norm_gamma = norm_gamma;
-  p.norm_out = reinterpret_cast<__nv_bfloat16*>(norm_out);
+  p.norm_out = reinterpret_cast<__half*>(norm_out);
   p.kps = (BK == 32 && p.kblocks_per_tap % 3 == 0) ? 3 : 1;
   p.a_block_bytes = (static_cast<uint32_t>(kConvBM * BK * 2) + 1023u) & ~1023u;
   p.b_block_bytes = (static_cast<uint32_t>(BN * BK * 2) + 1023u) & ~1023u;
@@ -595,20 +604,20 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
 extern "C" int mv_vae_conv(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
                            const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
                            int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
-                           int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
+                           int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off, int t_off,
                            mv_stream_t stream) {
   return vae_conv_impl(in_cl, in_T, in_H, in_W, Cin, w_packed, bias, res_cl, out, out_mode, out_T, out_H, out_W, Cout,
                        cout_real, ntaps, taps_dt_dh_dw, o_base, os_t, os_h, os_w, nsplit, nsplit_off, nullptr, nullptr,
-                       stream);
+                       t_off, stream);
 }
 
 extern "C" int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
                                  const float* bias, const void* res_cl, void* out, int out_T, int out_H, int out_W,
                                  int Cout, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t,
-                                 int64_t os_h, int64_t os_w, const float* norm_gamma, void* norm_out,
+                                 int64_t os_h, int64_t os_w, const float* norm_gamma, void* norm_out, int t_off,
                                  mv_stream_t stream) {
   return vae_conv_impl(in_cl, in_T, in_H, in_W, Cin, w_packed, bias, res_cl, out, 0, out_T, out_H, out_W, Cout, Cout,
-                       ntaps, taps_dt_dh_dw, o_base, os_t, os_h, os_w, 0, 0, norm_gamma, norm_out, stream);
+                       ntaps, taps_dt_dh_dw, o_base, os_t, os_h, os_w, 0, 0, norm_gamma, norm_out, t_off, stream);
 }
 
 extern "C" int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,
@@ -623,8 +632,8 @@ extern "C" int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* ga
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   if (blocks < 1) blocks = 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_cl);
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_cl);
+  const __half* x = reinterpret_cast<const __half*>(x_cl);
+  __half* y = reinterpret_cast<__half*>(y_cl);
   if (C <= 128) rmsnorm_silu_cl_kernel<16, 1><<<static_cast<int>(blocks), 256, 0, st>>>(x, y, gamma, nvox, C, silu);
   else if (C <= 256) rmsnorm_silu_cl_kernel<32, 1><<<static_cast<int>(blocks), 256, 0, st>>>(x, y, gamma, nvox, C, silu);
   else rmsnorm_silu_cl_kernel<32, 2><<<static_cast<int>(blocks), 256, 0, st>>>(x, y, gamma, nvox, C, silu);
@@ -640,17 +649,17 @@ extern "C" int mv_vae_latent_in(const float* z, const float* W2, const float* b2
   int64_t blocks = (nvox + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   vae_latent_in_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      z, W2, b2, mean, stdv, reinterpret_cast<__nv_bfloat16*>(out_cl), Z, nvox);
+      z, W2, b2, mean, stdv, reinterpret_cast<__half*>(out_cl), Z, nvox);
   MV_CHECK_LAUNCH("vae_latent_in_kernel");
   return MV_OK;
 }
 
-extern "C" int mv_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int M, int N, float scale,
+extern "C" int mv_softmax_rows(const float* S, int64_t lds, void* P_f16, int64_t ldp, int M, int N, float scale,
                                mv_stream_t stream) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(M > 0 && N > 0, "mv_softmax_rows: empty problem");
-  softmax_rows_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, reinterpret_cast<__nv_bfloat16*>(P_bf16),
+  softmax_rows_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, reinterpret_cast<__half*>(P_f16),
                                                                        ldp, N, scale);
   MV_CHECK_LAUNCH("softmax_rows_kernel");
   return MV_OK;

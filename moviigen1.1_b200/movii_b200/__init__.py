@@ -28,6 +28,7 @@ _ptr = _c.c_void_p
 # name -> argtypes (restype is always int); mirrors include/movii_b200.h one to one
 _SIGNATURES = {
     "mv_gemm_bf16": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int, _int, _int, _int, _ptr],
+    "mv_gemm_f16": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int, _int, _int, _int, _ptr],
     "mv_attention_fwd": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr],
     "mv_ln_modulate": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _f32, _int, _ptr],
     "mv_rmsnorm_rope": [_ptr, _i64, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
@@ -39,9 +40,9 @@ _SIGNATURES = {
     "mv_head_tokens": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _f32, _ptr],
     "mv_unpatchify": [_ptr, _ptr, _int, _int, _int, _int, _int, _int, _ptr],
     "mv_vae_conv": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _int, _int,
-                    _ptr, _i64, _i64, _i64, _i64, _int, _i64, _ptr],
+                    _ptr, _i64, _i64, _i64, _i64, _int, _i64, _int, _ptr],
     "mv_vae_conv_fused": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _ptr, _i64,
-                          _i64, _i64, _i64, _ptr, _ptr, _ptr],
+                          _i64, _i64, _i64, _ptr, _ptr, _int, _ptr],
     "mv_vae_rmsnorm_silu": [_ptr, _ptr, _ptr, _i64, _int, _int, _ptr],
     "mv_vae_latent_in": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _ptr],
     "mv_softmax_rows": [_ptr, _i64, _ptr, _i64, _int, _int, _f32, _ptr],
@@ -157,6 +158,20 @@ def gemm(a, w, bias, out, epilogue, gate=None):
     _req(out, want, "out")
     _call("mv_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
                               M, N, K, epilogue, _stream())
+    return out
+
+
+def gemm_f16(a, w, bias, out, epilogue):
+    """gemm() with fp16 operands; out fp16 (MV_EPI_BF16 slot) or fp32 (MV_EPI_F32).  WanVAE attention."""
+    _req(a, torch.float16, "a"); _req(w, torch.float16, "w"); _req(bias, torch.float32, "bias")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+    assert epilogue in (MV_EPI_BF16, MV_EPI_F32)
+    _req(out, torch.float32 if epilogue == MV_EPI_F32 else torch.float16, "out")
+    _call("mv_gemm_f16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), None, M, N, K,
+          epilogue, _stream())
     return out
 
 
@@ -337,25 +352,27 @@ def unpatchify(tokens, out, grid, patch_hw=(2, 2)):
     return out
 
 
-def vae_conv(x, conv, out, res=None, o_base=0, os_t=0, os_h=0, os_w=0, nsplit=0, nsplit_off=0, out_mode=0):
-    """x [T,H,W,Cin] bf16 channels-last (contiguous); conv: packed weights (.w [Cout,taps,Cin] bf16, .b fp32, .taps int8
-    CPU [ntaps,3]); out: bf16 channels-last (mode 0, any size — addressing by o_base/os_*) or fp32 [3,T,H,W] (mode 1)."""
-    _req(x, torch.bfloat16, "x"); _req(conv.w, torch.bfloat16, "w"); _req(conv.b, torch.float32, "bias")
-    _req(res, torch.bfloat16, "res")
+def vae_conv(x, conv, out, res=None, o_base=0, os_t=0, os_h=0, os_w=0, nsplit=0, nsplit_off=0, out_mode=0, t_off=0):
+    """x [t_off + T,H,W,Cin] fp16 channels-last (contiguous; the first t_off frames are the cached tail of the previous
+    temporal chunk); conv: packed weights (.w [Cout,taps,Cin] fp16, .b fp32, .taps int8 CPU [ntaps,3]); out: fp16
+    channels-last (mode 0, any size — addressing by o_base/os_*) or the fp32 video (mode 1, see movii_b200.h)."""
+    _req(x, torch.float16, "x"); _req(conv.w, torch.float16, "w"); _req(conv.b, torch.float32, "bias")
+    _req(res, torch.float16, "res")
     assert x.dim() == 4 and x.is_contiguous() and out.is_contiguous() and conv.w.is_contiguous()
-    T, H, W, Cin = x.shape
-    assert Cin == conv.cin and conv.taps.device.type == "cpu" and conv.taps.dtype == torch.int8
-    _req(out, torch.float32 if out_mode == 1 else torch.bfloat16, "out")
+    Tin, H, W, Cin = x.shape
+    T = Tin - int(t_off)
+    assert T > 0 and Cin == conv.cin and conv.taps.device.type == "cpu" and conv.taps.dtype == torch.int8
+    _req(out, torch.float32 if out_mode == 1 else torch.float16, "out")
     if res is not None:
-        assert res.is_contiguous() and res.numel() == out.numel()
-    _call("mv_vae_conv", _p(x), T, H, W, Cin, _p(conv.w), _p(conv.b), _p(res), _p(out), int(out_mode), T, H, W,
+        assert res.is_contiguous()
+    _call("mv_vae_conv", _p(x), Tin, H, W, Cin, _p(conv.w), _p(conv.b), _p(res), _p(out), int(out_mode), T, H, W,
           conv.cout, conv.cout_real, conv.ntaps, conv.taps.data_ptr(), int(o_base), int(os_t), int(os_h), int(os_w),
-          int(nsplit), int(nsplit_off), _stream())
+          int(nsplit), int(nsplit_off), int(t_off), _stream())
     return out
 
 
 def vae_rmsnorm_silu(x, out, gamma, silu=True):
-    _req(x, torch.bfloat16, "x"); _req(out, torch.bfloat16, "out"); _req(gamma, torch.float32, "gamma")
+    _req(x, torch.float16, "x"); _req(out, torch.float16, "out"); _req(gamma, torch.float32, "gamma")
     assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and gamma.numel() == x.shape[-1]
     C = x.shape[-1]
     _call("mv_vae_rmsnorm_silu", _p(x), _p(out), _p(gamma), x.numel() // C, C, int(bool(silu)), _stream())
@@ -366,7 +383,7 @@ def vae_latent_in(z, w2, b2, mean, std, out):
     for t, n in ((z, "z"), (w2, "w2"), (b2, "b2"), (mean, "mean"), (std, "std")):
         _req(t, torch.float32, n)
         assert t.is_contiguous()
-    _req(out, torch.bfloat16, "out")
+    _req(out, torch.float16, "out")
     Z = z.shape[0]
     nvox = z.numel() // Z
     assert out.is_contiguous() and out.numel() == z.numel() and out.shape[-1] == Z
@@ -375,7 +392,7 @@ def vae_latent_in(z, w2, b2, mean, std, out):
 
 
 def softmax_rows(s, p, n, scale):
-    _req(s, torch.float32, "s"); _req(p, torch.bfloat16, "p")
+    _req(s, torch.float32, "s"); _req(p, torch.float16, "p")
     assert s.dim() == 2 and p.dim() == 2 and s.stride(1) == 1 and p.stride(1) == 1 and s.shape[0] == p.shape[0]
     assert s.shape[1] >= n and p.shape[1] >= n
     _call("mv_softmax_rows", _p(s), s.stride(0), _p(p), p.stride(0), s.shape[0], n, float(scale), _stream())
@@ -435,18 +452,19 @@ def attention_scatter(q, k, v, o_table, n_dst, src_rank, rows_per_rank, ldo, sof
           src_rank, rows_per_rank, int(ldo), Lq, Lk, H, float(softmax_scale), _stream())
 
 
-def vae_conv_fused(x, conv, out, gamma, norm_out, res=None, o_base=0, os_t=0, os_h=0, os_w=0):
-    """vae_conv (bf16 channels-last) that also writes norm_out = silu(rms_norm(out) * gamma); out may be None."""
-    _req(x, torch.bfloat16, "x"); _req(conv.w, torch.bfloat16, "w"); _req(conv.b, torch.float32, "bias")
-    _req(res, torch.bfloat16, "res"); _req(out, torch.bfloat16, "out"); _req(norm_out, torch.bfloat16, "norm_out")
+def vae_conv_fused(x, conv, out, gamma, norm_out, res=None, o_base=0, os_t=0, os_h=0, os_w=0, t_off=0):
+    """vae_conv (fp16 channels-last) that also writes norm_out = silu(rms_norm(out) * gamma); out may be None."""
+    _req(x, torch.float16, "x"); _req(conv.w, torch.float16, "w"); _req(conv.b, torch.float32, "bias")
+    _req(res, torch.float16, "res"); _req(out, torch.float16, "out"); _req(norm_out, torch.float16, "norm_out")
     _req(gamma, torch.float32, "gamma")
     assert x.dim() == 4 and x.is_contiguous() and norm_out.is_contiguous() and conv.w.is_contiguous()
-    assert out is None or (out.is_contiguous() and out.numel() == norm_out.numel())
-    T, H, W, Cin = x.shape
-    assert Cin == conv.cin and gamma.numel() == conv.cout and conv.cout == conv.cout_real
-    _call("mv_vae_conv_fused", _p(x), T, H, W, Cin, _p(conv.w), _p(conv.b), _p(res), _p(out), T, H, W, conv.cout,
+    assert out is None or out.is_contiguous()
+    Tin, H, W, Cin = x.shape
+    T = Tin - int(t_off)
+    assert T > 0 and Cin == conv.cin and gamma.numel() == conv.cout and conv.cout == conv.cout_real
+    _call("mv_vae_conv_fused", _p(x), Tin, H, W, Cin, _p(conv.w), _p(conv.b), _p(res), _p(out), T, H, W, conv.cout,
           conv.ntaps, conv.taps.data_ptr(), int(o_base), int(os_t), int(os_h), int(os_w), _p(gamma), _p(norm_out),
-          _stream())
+          int(t_off), _stream())
     return norm_out
 
 

@@ -5,10 +5,12 @@ Scope: the DECODER (WanVAE.decode) — the encoder is preprocessing only and out
 The decode is one pass over the whole latent sequence (the reference's 21 single-frame chunks + feature cache are
 a causal network; the only irregularity — upsample3d's time_conv starting at frame 1, the 'Rep' branch — is
 reproduced exactly; SURVEY.md Appendix B, pinned by tests/golden/vae_*.pt).
-Activations are channels-last bf16 [T, H, W, C]; accumulation is fp32.
+Activations and conv operands are channels-last FP16 [T, H, W, C] (the 10 mantissa bits the reference's TF32 convs keep;
+max-abs 4e-3 against the fp32 reference, bf16 storage measured 3e-2); accumulation is fp32.
 """
 import logging
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -17,7 +19,7 @@ import movii_b200 as mv
 
 __all__ = ["WanVAE"]
 
-BF16, F32 = torch.bfloat16, torch.float32
+F16, F32 = torch.float16, torch.float32
 
 VAE_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632,
             -0.1922, -0.9497, 0.2503, -0.2921]
@@ -125,7 +127,7 @@ def _taps(kt, kh, kw):
 
 
 class _Conv:
-    """One packed convolution: bf16 [Cout_pad][taps][Cin] + fp32 bias + tap offsets."""
+    """One packed convolution: fp16 [Cout_pad][taps][Cin] + fp32 bias + tap offsets."""
 
     def __init__(self, weight, bias, taps, device, cout_pad=None):
         cout, cin = weight.shape[0], weight.shape[1]
@@ -134,7 +136,7 @@ class _Conv:
         cp = cout_pad or ((cout + 15) // 16 * 16)
         if cp != cout:
             w = torch.cat([w, w.new_zeros(cp - cout, *w.shape[1:])])
-        self.w = w.to(BF16).contiguous().to(device)
+        self.w = w.to(F16).contiguous().to(device)
         b = None if bias is None else bias.detach().to(F32)
         if b is not None and cp != cout:
             b = torch.cat([b, b.new_zeros(cp - cout)])
@@ -191,9 +193,15 @@ class VaeEngine:
                 if m.mode == "upsample3d":
                     up["time"] = _Conv(m.time_conv.weight, m.time_conv.bias, _taps(3, 1, 1), dev)
                 self.layers.append(("up", up))
-        self.fuse_next = False
+        self.operand_dtype = "f16"
         self.head_gamma = f32(d.head[0].gamma.reshape(-1))
         self.head = _Conv(d.head[2].weight, d.head[2].bias, _taps(3, 3, 3), dev, cout_pad=16)
+        # temporal chunk (latent frames per pass): the decoder is a causal network, every temporal conv carries the
+        # last two frames of its input to the next chunk — the reference's feature cache (vae.py:28-36,205-217) with
+        # chunks of `chunk` latent frames instead of one.  Bounds the live activations (1080P: 3 stage-D tensors of
+        # 16 frames instead of 81).
+        self.chunk = max(1, int(os.environ.get("MOVII_VAE_CHUNK", "4")))
+        self.cache = {}
 
     def _res(self, m):
         dev = self.device
@@ -204,13 +212,29 @@ class VaeEngine:
                     sc=None if isinstance(m.shortcut, nn.Identity) else
                     _Conv(m.shortcut.weight, m.shortcut.bias, _taps(1, 1, 1), dev))
 
+    # -- temporal feature cache ----------------------------------------------------------------------------
+    def halo_buffer(self, key, n, H, W, C):
+        """Input buffer of a temporal conv for an n-frame chunk: [k + n, H, W, C] whose first k (<= 2) frames are the
+        cached tail of the previous chunk's input; the producer writes frames [k:].  Returns (buffer, k)."""
+        cache = self.cache.get(key)
+        k = 0 if cache is None else cache.shape[0]
+        buf = torch.empty(k + n, H, W, C, dtype=F16, device=self.device)
+        if k:
+            buf[:k].copy_(cache)
+        return buf, k
+
+    def commit(self, key, buf):
+        """Remember the last two frames of this conv's input (cache + chunk) for the next chunk (vae.py:205-217)."""
+        self.cache[key] = buf[-2:].clone() if buf.shape[0] > 2 else buf.clone()
+
     # -- primitive launches -----------------------------------------------------------------------------
-    def conv(self, x, c, res=None, out=None):
-        """x [T,H,W,Cin] bf16 -> [T,H,W,Cout] bf16 (+res)."""
-        T, H, W, _ = x.shape
+    def conv(self, x, c, res=None, out=None, t_off=0):
+        """x [t_off + T,H,W,Cin] fp16 -> [T,H,W,Cout] fp16 (+res)."""
+        Tin, H, W, _ = x.shape
+        T = Tin - t_off
         if out is None:
-            out = torch.empty(T, H, W, c.cout, dtype=BF16, device=self.device)
-        mv.vae_conv(x, c, out, res=res, o_base=0, os_t=H * W * c.cout, os_h=W * c.cout, os_w=c.cout)
+            out = torch.empty(T, H, W, c.cout, dtype=F16, device=self.device)
+        mv.vae_conv(x, c, out, res=res, o_base=0, os_t=H * W * c.cout, os_h=W * c.cout, os_w=c.cout, t_off=t_off)
         return out
 
     def normsilu(self, x, gamma, out=None, silu=True):
@@ -221,31 +245,28 @@ class VaeEngine:
     # -- blocks -----------------------------------------------------------------------------------------------
     # Every conv of a ResidualBlock consumes silu(rms_norm(.)).  Where the producing conv holds a whole channel row
     # per thread (Cout <= 256: stages C and D, i.e. ~90 % of the bytes) that normalisation is fused into ITS epilogue
-    # (mv_vae_conv_fused) and the stand-alone pass over HBM disappears; `a_in` carries such a pre-normalised input.
+    # (mv_vae_conv_fused) and the stand-alone pass over HBM disappears.
     @staticmethod
     def _fusable(c):
         return c.cout <= 256 and c.cout == c.cout_real
 
-    def resblock(self, x, p, a_in=None, next_gamma=None):
-        """Returns (x_new, a_next): a_next = silu(rms_norm(x_new) * next_gamma) if it could be fused, else None."""
+    def resblock(self, x, p, key):
+        n, H, W, _ = x.shape
         h = x if p["sc"] is None else self.conv(x, p["sc"])
-        a = a_in if a_in is not None else self.normsilu(x, p["g0"], out=torch.empty_like(x))
-        T, H, W, _ = x.shape
         c2, c6 = p["c2"], p["c6"]
+        a, ka = self.halo_buffer(key + ".c2", n, H, W, c2.cin)
+        self.normsilu(x, p["g0"], out=a[ka:])
+        self.commit(key + ".c2", a)
+        y, ky = self.halo_buffer(key + ".c6", n, H, W, c2.cout)
         if self._fusable(c2):
-            y = torch.empty(T, H, W, c2.cout, dtype=BF16, device=self.device)
-            mv.vae_conv_fused(a, c2, None, p["g3"], y, o_base=0, os_t=H * W * c2.cout, os_h=W * c2.cout, os_w=c2.cout)
+            mv.vae_conv_fused(a, c2, None, p["g3"], y[ky:], o_base=0, os_t=H * W * c2.cout, os_h=W * c2.cout, os_w=c2.cout,
+                              t_off=ka)
         else:
-            y = self.conv(a, c2)
-            self.normsilu(y, p["g3"])
+            self.conv(a, c2, out=y[ky:], t_off=ka)
+            self.normsilu(y[ky:], p["g3"])
         del a
-        if next_gamma is not None and self._fusable(c6):
-            out = torch.empty(T, H, W, c6.cout, dtype=BF16, device=self.device)
-            a_next = torch.empty_like(out)
-            mv.vae_conv_fused(y, c6, out, next_gamma, a_next, res=h, o_base=0, os_t=H * W * c6.cout, os_h=W * c6.cout,
-                              os_w=c6.cout)
-            return out, a_next
-        return self.conv(y, c6, res=h), None
+        self.commit(key + ".c6", y)
+        return self.conv(y, c6, res=h, t_off=ky)
 
     def attention(self, x, p):
         """vae.py:223-262: per-frame single-head attention, d = C, over the H*W positions."""
@@ -256,79 +277,87 @@ class VaeEngine:
         del n
         k8 = (hw + 7) // 8 * 8
         S = torch.empty(hw, (hw + 3) // 4 * 4, dtype=F32, device=self.device)
-        P = torch.zeros(hw, k8, dtype=BF16, device=self.device)
-        vT = torch.zeros(C, k8, dtype=BF16, device=self.device)
-        O = torch.empty(T, H, W, C, dtype=BF16, device=self.device)
+        P = torch.zeros(hw, k8, dtype=F16, device=self.device)
+        vT = torch.zeros(C, k8, dtype=F16, device=self.device)
+        O = torch.empty(T, H, W, C, dtype=F16, device=self.device)
         Of = O.view(T * hw, C)
         scale = 1.0 / math.sqrt(C)
         for f in range(T):
             rows = qkv[f * hw:(f + 1) * hw]
-            mv.gemm(rows[:, 0:C], rows[:, C:2 * C], None, S[:, :hw], mv.MV_EPI_F32)
+            mv.gemm_f16(rows[:, 0:C], rows[:, C:2 * C], None, S[:, :hw], mv.MV_EPI_F32)
             mv.softmax_rows(S[:, :hw], P, hw, scale)
             vT[:, :hw].copy_(rows[:, 2 * C:3 * C].t())       # layout change only (K-major operand for P.V)
-            mv.gemm(P, vT, None, Of[f * hw:(f + 1) * hw], mv.MV_EPI_BF16)
+            mv.gemm_f16(P, vT, None, Of[f * hw:(f + 1) * hw], mv.MV_EPI_BF16)
         return self.conv(O, p["proj"], res=x)
 
-    def upsample(self, x, p, next_gamma=None):
+    def upsample(self, x, p, key, first):
         T, H, W, C = x.shape
-        if p["mode"] == "upsample3d" and T > 1:
-            T2 = 2 * T - 1
-            y = torch.empty(T2, H, W, C, dtype=BF16, device=self.device)
-            y[0].copy_(x[0])                                                            # 'Rep': frame 0 passes through
+        if p["mode"] == "upsample3d":
+            # time_conv (3,1,1) C -> 2C + frame interleave; its stream starts at frame 1 of the sequence and never
+            # sees frame 0, which passes through (the 'Rep' branch, vae.py:106-131)
+            src = x[1:] if first else x
+            nt = src.shape[0]
+            T2 = 2 * nt + (1 if first else 0)
+            y = torch.empty(T2, H, W, C, dtype=F16, device=self.device)
             fe = H * W * C
-            mv.vae_conv(x[1:], p["time"], y, res=None, o_base=fe, os_t=2 * fe, os_h=W * C, os_w=C, nsplit=C,
-                        nsplit_off=fe)
+            if first:
+                y[0].copy_(x[0])
+            if nt > 0:
+                xin, k = self.halo_buffer(key + ".t", nt, H, W, C)
+                xin[k:].copy_(src)                               # stage A / B tensors: a small copy
+                self.commit(key + ".t", xin)
+                mv.vae_conv(xin, p["time"], y, res=None, o_base=fe if first else 0, os_t=2 * fe, os_h=W * C, os_w=C,
+                            nsplit=C, nsplit_off=fe, t_off=k)
             x = y
             T = T2
         Co = C // 2
-        out = torch.empty(T, 2 * H, 2 * W, Co, dtype=BF16, device=self.device)
-        a_next = None
-        fuse = next_gamma is not None and all(self._fusable(c) for c in p["par"].values())
-        if fuse:
-            a_next = torch.empty_like(out)
+        out = torch.empty(T, 2 * H, 2 * W, Co, dtype=F16, device=self.device)
         for (a, b), c in p["par"].items():
-            kw = dict(o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co, os_w=2 * Co)
-            if fuse:
-                mv.vae_conv_fused(x, c, out, next_gamma, a_next, **kw)
-            else:
-                mv.vae_conv(x, c, out, res=None, **kw)
-        return out, a_next
+            mv.vae_conv(x, c, out, res=None, o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co,
+                        os_w=2 * Co)
+        return out
 
     # -- WanVAE.decode for one latent ---------------------------------------------------------------------------
     def decode(self, z):
         """z [z_dim, T, h, w] fp32 -> [3, 1+4(T-1), 8h, 8w] fp32 in [-1, 1]."""
         Z, T, h, w = z.shape
         z = z.to(self.device, F32).contiguous()
-        x = torch.empty(T, h, w, Z, dtype=BF16, device=self.device)
-        mv.vae_latent_in(z, self.w2, self.b2, self.mean, self.std, x)
-        x = self.conv(x, self.conv1)
-        # Cross-layer fusion (the producer also emits the NEXT block's normalised input) removes one more HBM pass per
-        # block but keeps a fourth stage-sized tensor alive (1080P: 117 GB peak instead of 71 GB) for a 1 % gain, so it
-        # is off by default; the in-block fusion (conv -> norm -> conv) is always on.
-        fuse_next = self.fuse_next
-        a = None                                      # silu(rms_norm(x)) for the next consumer, when already fused
-        n = len(self.layers)
-        for i, (kind, p) in enumerate(self.layers):
-            # gamma of the norm the NEXT layer applies to this layer's output (None: attention / upsample read x raw)
-            if i + 1 < n:
-                nk, npar = self.layers[i + 1]
-                next_gamma = npar["g0"] if nk == "res" else None
-            else:
-                next_gamma = self.head_gamma
-            if not fuse_next:
-                next_gamma = None
-            if kind == "res":
-                x, a = self.resblock(x, p, a_in=a, next_gamma=next_gamma)
-            elif kind == "attn":
-                x, a = self.attention(x, p), None
-            else:
-                x, a = self.upsample(x, p, next_gamma=next_gamma)
-        if a is None:
-            a = self.normsilu(x, self.head_gamma)
-        x = a
-        T, H, W, _ = x.shape
-        video = torch.empty(3, T, H, W, dtype=F32, device=self.device)
-        mv.vae_conv(x, self.head, video, res=None, out_mode=1)
+        n_up3d = sum(1 for kind, p in self.layers if kind == "up" and p["mode"] == "upsample3d")
+        sp_up = sum(1 for kind, p in self.layers if kind == "up")
+        Tout = T
+        for _ in range(n_up3d):
+            Tout = 2 * Tout - 1
+        Ho, Wo = h << sp_up, w << sp_up
+        video = torch.empty(3, Tout, Ho, Wo, dtype=F32, device=self.device)
+        self.cache = {}
+        t_done = 0
+        try:
+            for c0 in range(0, T, self.chunk):
+                n = min(self.chunk, T - c0)
+                first = c0 == 0
+                zc = z[:, c0:c0 + n].contiguous()
+                x, k = self.halo_buffer("conv1", n, h, w, Z)
+                mv.vae_latent_in(zc, self.w2, self.b2, self.mean, self.std, x[k:])
+                self.commit("conv1", x)
+                x = self.conv(x, self.conv1, t_off=k)
+                for i, (kind, p) in enumerate(self.layers):
+                    if kind == "res":
+                        x = self.resblock(x, p, "L%d" % i)
+                    elif kind == "attn":
+                        x = self.attention(x, p)
+                    else:
+                        x = self.upsample(x, p, "L%d" % i, first)
+                nt, H, W, C = x.shape
+                a, k = self.halo_buffer("head", nt, H, W, C)
+                self.normsilu(x, self.head_gamma, out=a[k:])
+                del x
+                self.commit("head", a)
+                mv.vae_conv(a, self.head, video, res=None, out_mode=1, o_base=t_done * H * W, os_t=Tout * H * W, t_off=k)
+                del a
+                t_done += nt
+        finally:
+            self.cache = {}
+        assert t_done == Tout
         return video
 
 

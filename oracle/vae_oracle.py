@@ -7,8 +7,8 @@ CausalConv3d sees two zero frames in front), except that each `upsample3d` appli
 only and passes frame 0 through (the 'Rep' branch, :106-131) — SURVEY.md Appendix B.  Pinned against outputs of the
 reference's own chunked decode for T = 1, 2, 3, 5 (tests/golden/vae_*.pt, oracle/make_golden.py).
 
-`rb` emulates the storage contract of the CUDA path (bf16 activations between layers, bf16 conv operands, fp32
-accumulation); rb = ident gives the reference's fp32 semantics.
+`rb` emulates the storage contract of the CUDA path (rb = f16_rt: fp16 activations between layers, fp16 conv operands,
+fp32 accumulation; bf16_rt: the round-1 contract, kept for comparison); rb = ident gives the reference's fp32 semantics.
 """
 import math
 
@@ -27,6 +27,11 @@ def ident(x):
 
 def bf16_rt(x):
     return x.to(torch.bfloat16).to(torch.float32)
+
+
+def f16_rt(x):
+    """fp16 round trip: the storage / operand contract of the CUDA decoder (csrc/vae_conv_sm100.cu)."""
+    return x.to(torch.float16).to(torch.float32)
 
 
 def causal_conv3d(x, w, b, rb=ident):

@@ -1,8 +1,9 @@
 """-m gpu parity of the native WanVAE decoder (implicit-GEMM tcgen05 convs) against golden outputs of the REFERENCE's
-chunked decode and against the CPU oracle.  Tolerance: the decoder runs with bf16 operands / activations where the
-reference uses fp32 storage and TF32 convolutions, so: PSNR >= 45 dB and max-abs <= 5e-2 on the [-1, 1] output
-(SURVEY.md §8c asked for 2e-2; the CPU emulation of the bf16 contract itself measures 2.3e-2..3.2e-2 with these
-unit-gain random weights — see DESIGN.md §5)."""
+chunked decode and against the CPU oracle.  Tolerance: PSNR >= 45 dB and max-abs <= 2e-2 on the
+[-1, 1] output.  The decoder runs with FP16 operands / activations (fp32 accumulation) where the reference uses fp32
+storage and TF32 convolutions; the CPU emulation of that contract measures max-abs 2e-3..4.3e-3 and PSNR 67-72 dB
+against the reference goldens (the bf16 contract of round 1 measured 1.4e-2..3.6e-2), so the bounds asserted here are
+the §8c ones with margin: max-abs <= 1e-2, PSNR >= 60 dB."""
 import math
 import os
 
@@ -40,12 +41,34 @@ def test_vae_decode_matches_reference_golden(vae, case):
     assert y.shape == ref.shape and y.dtype == torch.float32
     assert torch.isfinite(y).all() and y.abs().max() <= 1.0
     sd = state_dict_like(g["param_shapes"], g["seed"])
-    emu = V.decode(sd, rec["z"], V.bf16_rt)
-    assert psnr(y, ref) >= 45.0, (psnr(y, ref), psnr(emu, ref))
-    assert (y - ref).abs().max().item() <= 5e-2, ((y - ref).abs().max().item(), (emu - ref).abs().max().item())
+    emu = V.decode(sd, rec["z"], V.f16_rt)
+    assert psnr(y, ref) >= 60.0, (psnr(y, ref), psnr(emu, ref))
+    assert (y - ref).abs().max().item() <= 1e-2, ((y - ref).abs().max().item(), (emu - ref).abs().max().item())
     # against the CPU emulation of the same storage contract (it differs in summation order and in the pre-summed
     # sub-pixel upsample weights): same error class as either one against the fp32 reference
-    assert psnr(y, emu) >= 46.0
+    assert psnr(y, emu) >= 60.0
+
+
+@pytest.mark.parametrize("case", [(5, 4, 4), (3, 4, 6)])
+def test_vae_temporal_chunking_is_exact(vae, case):
+    """The decode runs in temporal chunks with a two-frame feature cache per temporal conv (the reference's scheme,
+    vae.py:28-36,205-217, with larger chunks).  Any chunk size must give the SAME BITS as the whole-sequence pass:
+    same taps, same accumulation order, only the provenance of the two history frames differs — including chunk 1
+    (the reference's own chunking: frame 0 alone through the 'Rep' branch) and chunks that do not divide T."""
+    m, g = vae
+    rec = g["cases"][case]
+    eng = m.engine()
+    z = rec["z"].to(DEV)
+    keep = eng.chunk
+    try:
+        eng.chunk = 64
+        whole = eng.decode(z).clone()
+        for c in (1, 2, 3, 4):
+            eng.chunk = c
+            assert torch.equal(eng.decode(z), whole), c
+    finally:
+        eng.chunk = keep
+    assert (whole.cpu() - rec["y"].float()).abs().max().item() <= 1e-2
 
 
 def test_vae_conv_primitives(vae):
@@ -55,24 +78,24 @@ def test_vae_conv_primitives(vae):
     from wan.modules.vae import _Conv, _parity_convs, _taps
     g = torch.Generator().manual_seed(1)
     T, H, W, Ci, Co = 3, 11, 21, 96, 192
-    x = torch.randn(T, H, W, Ci, generator=g).bfloat16()
+    x = torch.randn(T, H, W, Ci, generator=g).half()
     wt = (torch.randn(Co, Ci, 3, 3, 3, generator=g) / math.sqrt(27 * Ci))
     b = torch.randn(Co, generator=g)
     c = _Conv(wt, b, _taps(3, 3, 3), DEV)
-    out = torch.empty(T, H, W, Co, dtype=torch.bfloat16, device=DEV)
+    out = torch.empty(T, H, W, Co, dtype=torch.float16, device=DEV)
     mv.vae_conv(x.to(DEV), c, out, o_base=0, os_t=H * W * Co, os_h=W * Co, os_w=Co)
-    ref = V.causal_conv3d(x.float().permute(3, 0, 1, 2)[None], wt, b, V.bf16_rt)[0].permute(1, 2, 3, 0)
+    ref = V.causal_conv3d(x.float().permute(3, 0, 1, 2)[None], wt, b, V.f16_rt)[0].permute(1, 2, 3, 0)
     err = (out.float().cpu() - ref).abs().max().item()
-    assert err <= 3e-2, err
+    assert err <= 4e-3, err      # fp16 output rounding of O(1) values: 2^-11 relative
     # sub-pixel upsample: nearest-exact x2 + Conv2d 3x3
     w2 = torch.randn(Co // 2, Co, 3, 3, generator=g) / math.sqrt(9 * Co)
     b2 = torch.randn(Co // 2, generator=g)
-    xin = torch.randn(T, H, W, Co, generator=g).bfloat16()
-    up = torch.empty(T, 2 * H, 2 * W, Co // 2, dtype=torch.bfloat16, device=DEV)
+    xin = torch.randn(T, H, W, Co, generator=g).half()
+    up = torch.empty(T, 2 * H, 2 * W, Co // 2, dtype=torch.float16, device=DEV)
     for (a, bb), cc in _parity_convs(w2, b2, DEV).items():
         mv.vae_conv(xin.to(DEV), cc, up, o_base=(a * 2 * W + bb) * (Co // 2), os_t=4 * H * W * (Co // 2),
                     os_h=4 * W * (Co // 2), os_w=2 * (Co // 2))
     xf = F.interpolate(xin.float().permute(0, 3, 1, 2), scale_factor=(2.0, 2.0), mode="nearest-exact")
-    ref2 = F.conv2d(xf, V.bf16_rt(w2), b2, padding=1).permute(0, 2, 3, 1)
+    ref2 = F.conv2d(xf, V.f16_rt(w2), b2, padding=1).permute(0, 2, 3, 1)
     err2 = (up.float().cpu() - ref2).abs().max().item()
-    assert err2 <= 3e-2, err2
+    assert err2 <= 6e-3, err2    # four pre-summed fp16 sub-pixel kernels vs one 3x3 kernel on the upsampled image
