@@ -237,6 +237,10 @@ int mv_attention_fwd_trace(const void* q, int64_t ldq, const void* k, int64_t ld
                            int64_t ldo, int Lq, int Lk, int H, float softmax_scale, unsigned long long* trace,
                            int trace_steps, mv_stream_t stream);
 
+/* Diagnostics only: 1 = route the large GEMMs to the CTA-pair (cta_group::2, 256 x 256 tile) kernel, 0 = single-CTA
+ * 128 x 256 tiles, negative = keep (default: MV_GEMM_PAIR or the built-in default).  A/B timing inside one process. */
+int mv_gemm_config(int pair);
+
 /* Diagnostics only: overrides the attention kernel variant chosen from the environment (MV_ATTN_KSTEP / _EMU / _STALE /
  * _PINGPONG / _SKEW) for A/B timing inside one process; a negative argument keeps the current value.  kstep 64 | 128,
  * emu 0..2 (fraction of exponentials on the FMA pipe: none, 1/4, 1/2), stale 1 = fixed-reference softmax (128-key

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "mv_sinusoid_embed": [_ptr, _int, _ptr, _int, _ptr],
     "mv_attention_fwd_trace": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr, _int, _ptr],
     "mv_attention_config": [_int, _int, _int, _int, _int],
+    "mv_gemm_config": [_int],
     "mv_t5_attention": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _int, _ptr],
     "mv_t5_rmsnorm": [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _f32, _ptr],
     "mv_embed_gather": [_ptr, _i64, _i64, _ptr, _ptr, _i64, _int, _int, _ptr],
@@ -526,6 +527,11 @@ def attention_trace(q, k, v, out, trace, softmax_scale=None):
           Lq, k.shape[0], H, float(softmax_scale if softmax_scale is not None else 128 ** -0.5), _p(trace),
           trace.shape[1], _stream())
     return out
+
+
+def gemm_config(pair=-1):
+    """Diagnostics: 1 = CTA-pair (cta_group::2) GEMM kernel for the large linears, 0 = single-CTA kernel."""
+    _check(lib().mv_gemm_config(int(pair)), "mv_gemm_config")
 
 
 def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, skew=-1):

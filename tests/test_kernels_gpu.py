@@ -176,6 +176,68 @@ def test_attention_running_max_growth(mv, jumps, offset):
     assert rel_l2(out.float(), ref) <= 5e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 64), (1300, 768, 192), (2048, 1000, 320), (4096, 5120, 1024),
+                                   (1025, 520, 72)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_cta_pair(mv, M, N, K, epi):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tile over two SMs, each CTA staging half of the W tile)
+    against the oracle: full tiles, ragged M (a pair whose second CTA is partly / entirely out of range), ragged N."""
+    g = torch.Generator().manual_seed(M + N * 3 + K + epi)
+    a = (torch.randn(M, K, generator=g)).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, generator=g)
+    y = O.bf16_rt(a.float() @ w.float().t() + bias)
+    mv.gemm_config(1)
+    try:
+        if epi in (0, 1):
+            ref = y if epi == 0 else O.bf16_rt(O.gelu_tanh(y))
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+            mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi)
+            gate = None
+        elif epi == 2:
+            x0 = torch.randn(M, N, generator=g)
+            gate = torch.randn(N, generator=g)
+            ref = x0 + y * gate
+            out = x0.to(DEV)
+            mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi, gate=gate.to(DEV))
+        else:
+            ref = y
+            gate = None
+            out = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+            mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi)
+        torch.cuda.synchronize()
+    finally:
+        mv.gemm_config(0)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) <= 3e-3
+    err = (out.float().cpu() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2 * (1 if epi != 2 else 1 + gate.abs().max().item())
+    assert (err <= tol).all(), err.max().item()
+
+
+def test_gemm_cta_pair_ksplit_equals_single_cta(mv):
+    """K-split A operand (the Ulysses return layout) through the pair kernel == the single-CTA kernel, bit for bit
+    (same K order, same fp32 accumulation)."""
+    g = torch.Generator().manual_seed(11)
+    P, M, Kb, N = 4, 1500, 128, 768
+    a = torch.randn(P, M, Kb, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(N, P * Kb, generator=g) / math.sqrt(P * Kb)).bfloat16().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    outs = []
+    for pair in (0, 1):
+        mv.gemm_config(pair)
+        try:
+            o = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+            mv.gemm_ksplit(a, w, bias, o, 0)
+            torch.cuda.synchronize()
+        finally:
+            mv.gemm_config(0)
+        outs.append(o)
+    ref = O.bf16_rt(a.permute(1, 0, 2).reshape(M, P * Kb).float().cpu() @ w.float().cpu().t() + bias.cpu())
+    assert rel_l2(outs[1].float(), ref) <= 3e-3
+    assert torch.equal(outs[0], outs[1])
+
+
 # ---------------------------------------------------------------------------------------------- rowops
 @pytest.mark.parametrize("M,C", [(7, 128), (33, 5120), (5, 1536)])
 @pytest.mark.parametrize("variant", ["plain", "mod", "affine", "round_mod"])

@@ -37,16 +37,25 @@ def timeit(fn, iters=5, warmup=2):
 
 
 def bench_gemm(M, N, K, epi=0):
+    """Both tilings of mv_gemm_bf16 (single CTA 128x256, CTA pair 256x256) and cuBLAS (F.linear, bf16 out — it does
+    LESS epilogue work than epi 1 / 2) on the same operands."""
     a = torch.randn(M, K, device=DEV).bfloat16()
     w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device=DEV)
     f32 = epi in (2, 3)
     out = torch.zeros(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=DEV)
-    ms = timeit(lambda: mv.gemm(a, w, bias, out, epi))
+    gate = torch.randn(N, device=DEV) if epi == 2 else None
+    res = {}
+    for pair in (0, 1):
+        mv.gemm_config(pair)
+        res[pair] = timeit(lambda: mv.gemm(a, w, bias, out, epi, gate=gate))
+    mv.gemm_config(-1)
     ms_ref = timeit(lambda: torch.nn.functional.linear(a, w, bias.bfloat16()))
     fl = 2.0 * M * N * K
-    print(json.dumps(dict(kind="gemm", M=M, N=N, K=K, epi=epi, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
-                          cublas_ms=round(ms_ref, 4), cublas_tflops=round(fl / ms_ref / 1e9, 1))), flush=True)
+    print(json.dumps(dict(kind="gemm", M=M, N=N, K=K, epi=epi, ms=round(res[0], 4), tflops=round(fl / res[0] / 1e9, 1),
+                          pair_ms=round(res[1], 4), pair_tflops=round(fl / res[1] / 1e9, 1),
+                          cublas_ms=round(ms_ref, 4), cublas_tflops=round(fl / ms_ref / 1e9, 1),
+                          best_vs_cublas=round(ms_ref / min(res.values()), 3))), flush=True)
 
 
 def bench_attn(L, H, Lk=None):
@@ -82,6 +91,25 @@ def bench_rowops(M=75600, C=5120):
     ms = timeit(lambda: mv.rmsnorm_rope(qk, wt, cs))
     gb = (M * C * 4 + M * 512) / 1e9
     print(json.dumps(dict(kind="rmsnorm_rope", M=M, C=C, ms=round(ms, 4), gbs=round(gb / ms * 1e3, 1))), flush=True)
+    qkv = torch.randn(M, 3 * C, device=DEV).bfloat16()
+    wk = torch.randn(C, device=DEV)
+    ms = timeit(lambda: mv.qkv_norm_rope(qkv, wt, wk, cs))
+    gb = (2 * M * C * 4 + M * 512) / 1e9           # q and k read + written once (bf16), one cos/sin row per token
+    print(json.dumps(dict(kind="qkv_norm_rope (q+k, one launch)", M=M, C=C, ms=round(ms, 4),
+                          gbs=round(gb / ms * 1e3, 1))), flush=True)
+    P = 8
+    bufs = [torch.empty(P, M, C // P, dtype=torch.bfloat16, device=DEV) for _ in range(3)]
+    tabs = tuple(mv.ptr_table([b[d].data_ptr() for d in range(P)]) for b in bufs)
+    ms = timeit(lambda: mv.qkv_norm_rope(qkv, wt, wk, cs, dst=tabs, n_dst=P, src_slot=0))
+    gb = (3 * M * C * 4 + M * 512) / 1e9
+    print(json.dumps(dict(kind="qkv_norm_rope (q+k+v scatter, local)", M=M, C=C, ms=round(ms, 4),
+                          gbs=round(gb / ms * 1e3, 1))), flush=True)
+    lat = [torch.randn(16 * 21 * 90 * 160, device=DEV) for _ in range(9)]
+    coef = [5.0, 0.9, 1.0, 2.0, 0.9, 0.1, 0.2, 0.5, 1.1, 0.0, 0.5, 0.0, 2.0, 0.9, 0.1, 0.2, 1.1, 0.0, 0.5, 0.0]
+    ms = timeit(lambda: mv.unipc_cfg_step(lat[0], lat[1], lat[2], lat[3], [lat[4], lat[5], None], coef, lat[6], lat[7],
+                                          lat[8]))
+    gb = lat[0].numel() * 4 * 9 / 1e9
+    print(json.dumps(dict(kind="unipc_cfg_step (720P latent)", ms=round(ms, 4), gbs=round(gb / ms * 1e3, 1))), flush=True)
 
 
 if __name__ == "__main__":
