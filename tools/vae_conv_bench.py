@@ -1,0 +1,78 @@
+"""Per-shape timing of the WanVAE implicit-GEMM convolution (mv_vae_conv / mv_vae_conv_fused) at the decoder's 1080P
+stage shapes, one temporal chunk of 4 latent frames: TFLOP/s per conv shape, so that the slow
+shapes are visible; also the single-launch driver for `ncu --set full -k regex:conv_igemm`.
+Usage: python tools/vae_conv_bench.py [stage ...]   stage in A B C D up2 (default: all)."""
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "moviigen1.1_b200"))
+import movii_b200 as mv  # noqa: E402
+from wan.modules.vae import _Conv, _parity_convs, _taps  # noqa: E402
+
+DEV = "cuda"
+# stage: (frames of one 4-latent-frame chunk, H, W, Cin, Cout)
+STAGES = {"A": (4, 104, 240, 384, 384), "B": (8, 208, 480, 384, 384), "C": (16, 416, 960, 192, 192),
+          "D": (16, 832, 1920, 96, 96)}
+
+
+def timeit(fn, iters=3):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    which = sys.argv[1:] or ["A", "B", "C", "D", "up2"]
+    mv.device_check()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for st in which:
+        if st == "up2":        # upsamples.11: nearest-2x + Conv2d 192 -> 96 as four 2x2 sub-pixel convs (stage C -> D)
+            T, H, W, Ci = 16, 416, 960, 192
+            x = torch.randn(T, H, W, Ci, device=DEV, generator=g).half()
+            w2 = torch.randn(Ci // 2, Ci, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Ci)
+            par = _parity_convs(w2.cpu(), torch.zeros(Ci // 2), DEV)
+            Co = Ci // 2
+            out = torch.empty(T, 2 * H, 2 * W, Co, dtype=torch.float16, device=DEV)
+
+            def run():
+                for (a, b), c in par.items():
+                    mv.vae_conv(x, c, out, o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co, os_w=2 * Co)
+            ms = timeit(run)
+            fl = 2.0 * 16 * Ci * Co * T * H * W            # 4 parities x 4 taps, as executed
+            print(json.dumps(dict(kind="vae_up2d_subpixel", shape=[T, H, W, Ci, Co], ms=round(ms, 3),
+                                  tflops_executed=round(fl / ms / 1e9, 1))), flush=True)
+            continue
+        T, H, W, Ci, Co = STAGES[st]
+        x = torch.randn(T + 2, H, W, Ci, device=DEV, generator=g).half()
+        wt = torch.randn(Co, Ci, 3, 3, 3, device=DEV, generator=g) / math.sqrt(27 * Ci)
+        c = _Conv(wt.cpu(), torch.zeros(Co), _taps(3, 3, 3), DEV)
+        out = torch.empty(T, H, W, Co, dtype=torch.float16, device=DEV)
+        res = torch.randn(T, H, W, Co, device=DEV, generator=g).half()
+        gamma = torch.ones(Co, device=DEV)
+        kw = dict(o_base=0, os_t=H * W * Co, os_h=W * Co, os_w=Co, t_off=2)
+        fl = 2.0 * 27 * Ci * Co * T * H * W
+        ms = timeit(lambda: mv.vae_conv(x, c, out, res=res, **kw))
+        rec = dict(kind="vae_conv3x3x3", stage=st, shape=[T, H, W, Ci, Co], ms=round(ms, 3), tflops=round(fl / ms / 1e9, 1))
+        if Co <= 256:
+            nout = torch.empty_like(out)
+            ms2 = timeit(lambda: mv.vae_conv_fused(x, c, None, gamma, nout, **kw))
+            rec.update(fused_ms=round(ms2, 3), fused_tflops=round(fl / ms2 / 1e9, 1))
+        print(json.dumps(rec), flush=True)
+        del x, out, res
+
+
+if __name__ == "__main__":
+    main()
