@@ -45,6 +45,7 @@ struct GemmParams {
   int64_t ldo;
   int M, N, K;
   int num_m, num_n, num_tiles, num_kb;
+  int group_m;   // M tiles per raster group (tile order: all N tiles of a group of group_m M tiles, M fastest)
   int a_kblock;  // > 0: A is split along K into blocks of a_kblock columns (3-D tensor map {k, m, block})
   int f16;         // 1: operands (and 16-bit outputs) are IEEE fp16 instead of bf16 (mv_gemm_f16: WanVAE attention)
   int stream_out;  // 1 (MV_GEMM_STREAM=1): ld/st.global.cs (evict-first) for the output and the fp32 residual, so that
@@ -53,11 +54,11 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
-  const int per_group = kGroupM * p.num_n;
+  const int per_group = p.group_m * p.num_n;
   const int g = tile / per_group;
   const int within = tile - g * per_group;
-  const int gm = min(kGroupM, p.num_m - g * kGroupM);
-  m_blk = g * kGroupM + within % gm;
+  const int gm = min(p.group_m, p.num_m - g * p.group_m);
+  m_blk = g * p.group_m + within % gm;
   n_blk = within / gm;
 }
 
@@ -596,6 +597,14 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
     p.a_kblock = a_kblock;
     p.f16 = f16;
     p.stream_out = 0;
+    {
+      static int grp = -1;     // MV_GEMM_PAIR_GROUP: 256-row M tiles per raster group (default 8 = 2048 rows, the same
+      if (grp < 0) {           // A working set as the single-CTA kernel's 16 x 128)
+        const char* e = getenv("MV_GEMM_PAIR_GROUP");
+        grp = (e != nullptr && atoi(e) > 0) ? atoi(e) : 8;
+      }
+      p.group_m = grp;
+    }
     return dispatch_gemm_pair(tmA, tmBp, p, epilogue, static_cast<cudaStream_t>(stream));
   }
   // tile width: 256 unless that leaves SMs idle on a skinny problem (MV_GEMM_BN=64|256 forces one, for tests)
@@ -630,6 +639,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_block_stride, int a_k
   p.num_kb = (K + BK - 1) / BK;
   p.a_kblock = a_kblock;
   p.f16 = f16;
+  p.group_m = kGroupM;
   {
     static int stream = -1;   // MV_GEMM_STREAM=1 turns the evict-first accesses on; measured neutral (+-3 %), default off
     if (stream < 0) {

@@ -147,6 +147,15 @@ qkv_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __r
   }
   const float* csr = (pt.rope && cs != nullptr) ? cs + static_cast<int64_t>(row) * head_dim : nullptr;  // [half][2]
   const int cols_per_dst = a.n_dst > 0 ? C / a.n_dst : C;
+  // A lane's columns are lane*8 + 256*i: when head_dim divides 256 they sit at the SAME position inside every head, so
+  // the lane needs one set of 4 (cos, sin) pairs per row, not one per vector (2 loads instead of 2 * NV)
+  const bool cs_once = (256 % head_dim) == 0;
+  float c4[8];
+  if (csr != nullptr && cs_once) {
+    const float4* cp = reinterpret_cast<const float4*>(csr + ((lane << 3) % head_dim));
+    const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+    c4[0] = c0.x; c4[1] = c0.y; c4[2] = c0.z; c4[3] = c0.w; c4[4] = c1.x; c4[5] = c1.y; c4[6] = c1.z; c4[7] = c1.w;
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int idx = lane + 32 * i;
@@ -157,8 +166,7 @@ qkv_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __r
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + col) + 1);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      float c4[8];
-      if (csr != nullptr) {
+      if (csr != nullptr && !cs_once) {
         const float4* cp = reinterpret_cast<const float4*>(csr + (col % head_dim));   // 4 (cos, sin) pairs
         const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
         c4[0] = c0.x; c4[1] = c0.y; c4[2] = c0.z; c4[3] = c0.w; c4[4] = c1.x; c4[5] = c1.y; c4[6] = c1.z; c4[7] = c1.w;

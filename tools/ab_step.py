@@ -21,7 +21,8 @@ from wan.modules.model import WanModel  # noqa: E402
 def main():
     args = sys.argv[1:]
     workload = args[0] if args and args[0] in bench.WORKLOADS else "720p"
-    variants = [a for a in args if ":" in a] or ["128:0:1:0", "128:0:0:0", "64:1:0:0", "128:0:1:0"]
+    # variant = kstep:emu:stale:pingpong[:skew][,pair=0|1]   (pair: CTA-pair GEMM kernel for the large linears)
+    variants = [a for a in args if ":" in a] or ["128:0:1:0,pair=0", "128:0:1:0,pair=1", "128:0:1:0,pair=0"]
     dev = torch.device("cuda", 0)
     mv.device_check()
     cfg = Config(t2v_14B)
@@ -41,8 +42,13 @@ def main():
     t = torch.tensor([900], device=dev)
     ref = None
     for var in variants:
-        ks, emu, stale, pp, skew = (int(x) for x in (var.split(":") + ["0"])[:5])
+        attn_var, _, opts = var.partition(",")
+        ks, emu, stale, pp, skew = (int(x) for x in (attn_var.split(":") + ["0"])[:5])
         mv.attention_config(ks, emu, stale, pp, skew)
+        for o in [x for x in opts.split(",") if x]:
+            k, _, v = o.partition("=")
+            if k == "pair":
+                mv.gemm_config(int(v))
         out = model([lat], t=t, context=ctx, seq_len=seq_len)[0]
         torch.cuda.synchronize()
         sampler = bench.ClockSampler(0)
