@@ -215,6 +215,10 @@ int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W, int Cin, 
                       const int8_t* taps_dt_dh_dw, int64_t o_base, int64_t os_t, int64_t os_h, int64_t os_w,
                       const float* norm_gamma, void* norm_out, int t_off, mv_stream_t stream);
 
+/* Diagnostics only: 1 = route the tensor-bound convolutions to the CTA-pair kernel (cta_group::2, NT stacked tiles per
+ * CTA, one A box per (dt, dw)), 0 = the single-CTA kernel, -1 = keep, -2 = back to the default (MV_CONV_PAIR or built-in). */
+int mv_vae_conv_config(int pair, int tiles_per_cta /* 0 auto, 1 | 2 | 4 */);
+
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per voxel over channels (RMS_norm + nn.SiLU,
  * vae.py:39-54,194-199); channels-last fp16, in place allowed. */
 int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,
@@ -238,7 +242,7 @@ int mv_attention_fwd_trace(const void* q, int64_t ldq, const void* k, int64_t ld
                            int trace_steps, mv_stream_t stream);
 
 /* Diagnostics only: 1 = route the large GEMMs to the CTA-pair (cta_group::2, 256 x 256 tile) kernel, 0 = single-CTA
- * 128 x 256 tiles, negative = keep (default: MV_GEMM_PAIR or the built-in default).  A/B timing inside one process. */
+ * 128 x 256 tiles, -1 = keep, -2 = back to the default (MV_GEMM_PAIR or built-in).  A/B timing inside one process. */
 int mv_gemm_config(int pair);
 
 /* Diagnostics only: overrides the attention kernel variant chosen from the environment (MV_ATTN_KSTEP / _EMU / _STALE /

@@ -537,6 +537,7 @@ bool gemm_pair_enabled() {
 
 extern "C" int mv_gemm_config(int pair) {
   if (pair >= 0) g_gemm_pair = pair != 0 ? 1 : 0;
+  else if (pair == -2) g_gemm_pair = -1;   // back to MV_GEMM_PAIR / the built-in default
   return MV_OK;
 }
 

@@ -16,6 +16,9 @@
 // sub-pixel convolutions on the low-resolution input (vae.py:74-79: the nearest-exact x2 + 3x3 kernel collapses to
 // a 2x2 kernel per output parity, 2.25x fewer FLOPs and no upsampled intermediate), the temporal time_conv
 // (3,1,1) with its frame interleave (vae.py:84-85,128-137) and the 96->3 head conv with the final clamp.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -63,6 +66,149 @@ struct ConvCfg {
   static constexpr uint32_t kSBO = 8 * kRowBytes;
   static constexpr uint32_t kABytes = kConvBM * kRowBytes;
 };
+
+// Epilogue of one accumulator tile for ONE output voxel (t, h, w) = this thread's TMEM lane: bias, residual, store —
+// or, with norm_out, the consumer's RMS_norm + SiLU fused in (two passes over the TMEM row).  taddr = this warp's lane
+// quadrant + the tile's first accumulator column.
+__device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t taddr, int n_blk, int t, int h, int w) {
+  const bool ok = (h < p.H) && (w < p.W);
+  int n0 = n_blk * p.BN;
+  int64_t off = p.o_base + t * p.os_t + h * p.os_h + w * p.os_w;
+  int nb = n0;  // channel offset inside the destination row
+  if (p.nsplit > 0 && n0 >= p.nsplit) {
+    nb = n0 - p.nsplit;
+    off += p.nsplit_off;
+  }
+  if (p.norm_out != nullptr) {
+    // Fused RMS_norm + SiLU of the output row (vae.py:39-54,194-199): the whole channel row of this voxel sits in
+    // this thread's TMEM lane, so the consumer's normalised input is produced here and the stand-alone
+    // normalisation pass over HBM disappears.  Pass 1: bias/residual, sum of squares, (optional) raw store;
+    // pass 2: re-read TMEM, normalise, SiLU, store.
+    float ss = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const float inv = pass == 0 ? 0.f : sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 1
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c, v);
+        tc_wait_ld();
+        const int ncols = min(32, p.BN - c);
+        if (!ok) continue;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float b = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + c + i) : 0.f;
+          f[i] = i < ncols ? __uint_as_float(v[i]) + b : 0.f;
+        }
+        if (p.res != nullptr) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (8 * i < ncols) {
+              const uint4 q = r4[i];
+              const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                f[8 * i + 2 * k] += f16_lo(u[k]);
+                f[8 * i + 2 * k + 1] += f16_hi(u[k]);
+              }
+            }
+          }
+        }
+        __half* dst = nullptr;
+        if (pass == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            f[i] = f16_round(f[i]);      // statistics of the value as it is stored
+            ss += f[i] * f[i];
+          }
+          if (p.out != nullptr) dst = reinterpret_cast<__half*>(p.out) + off + c;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float gmm = i < ncols ? __ldg(p.norm_gamma + c + i) : 0.f;
+            const float y = f16_round(f[i]) * inv * gmm;
+            f[i] = y / (1.f + __expf(-y));
+          }
+          dst = p.norm_out + off + c;
+        }
+        if (dst != nullptr) {
+          uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (8 * i < ncols) {
+              uint4 q;
+              q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
+              q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
+              q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
+              q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
+              o4[i] = q;
+            }
+          }
+        }
+      }
+    }
+  } else
+  for (int c = 0; c < p.BN; c += 32) {   // BN multiple of 16: last chunk may be half valid
+    uint32_t v[32];
+    tmem_ld_x32(taddr + c, v);
+    tc_wait_ld();
+    const int ncols = min(32, p.BN - c);
+    if (ok) {
+      if (p.out_mode == 0) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float b = (p.bias != nullptr && i < ncols && n0 + c + i < p.Cout) ? __ldg(p.bias + n0 + c + i) : 0.f;
+          f[i] = __uint_as_float(v[i]) + b;
+        }
+        __half* o = reinterpret_cast<__half*>(p.out) + off + nb + c;
+        if (p.res != nullptr) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + nb + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (8 * i < ncols) {
+              const uint4 q = r4[i];
+              const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                f[8 * i + 2 * k] += f16_lo(u[k]);
+                f[8 * i + 2 * k + 1] += f16_hi(u[k]);
+              }
+            }
+          }
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (8 * i < ncols) {
+            uint4 q;
+            q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
+            q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
+            q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
+            q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
+            o4[i] = q;
+          }
+        }
+      } else {
+        // head conv: fp32 channel-first video, clamp(-1, 1)                       vae.py:660-661
+        float* o = reinterpret_cast<float*>(p.out);
+        const int64_t plane = p.os_t > 0 ? p.os_t : static_cast<int64_t>(p.T) * p.H * p.W;   // channel stride
+        const int64_t pos = p.o_base + (static_cast<int64_t>(t) * p.H + h) * p.W + w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (c == 0 && i < p.cout_real) {
+            float b = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+            float y = __uint_as_float(v[i]) + b;
+            y = fminf(1.f, fmaxf(-1.f, y));
+            o[i * plane + pos] = y;
+          }
+        }
+      }
+    }
+  }
+}
 
 template <int BK>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -188,145 +334,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       decode(tile, n_blk, t, h0, w0);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int h = h0 + (r >> 4), w = w0 + (r & 15);
-      const bool ok = (h < p.H) && (w < p.W);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256;
-      int n0 = n_blk * p.BN;
-      int64_t off = p.o_base + t * p.os_t + h * p.os_h + w * p.os_w;
-      int nb = n0;  // channel offset inside the destination row
-      if (p.nsplit > 0 && n0 >= p.nsplit) {
-        nb = n0 - p.nsplit;
-        off += p.nsplit_off;
-      }
-      if (p.norm_out != nullptr) {
-        // Fused RMS_norm + SiLU of the output row (vae.py:39-54,194-199): the whole channel row of this voxel sits in
-        // this thread's TMEM lane, so the consumer's normalised input is produced here and the stand-alone
-        // normalisation pass over HBM disappears.  Pass 1: bias/residual, sum of squares, (optional) raw store;
-        // pass 2: re-read TMEM, normalise, SiLU, store.
-        float ss = 0.f;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const float inv = pass == 0 ? 0.f : sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll 1
-          for (int c = 0; c < p.BN; c += 32) {
-            uint32_t v[32];
-            tmem_ld_x32(taddr + c, v);
-            tc_wait_ld();
-            const int ncols = min(32, p.BN - c);
-            if (!ok) continue;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float b = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + c + i) : 0.f;
-              f[i] = i < ncols ? __uint_as_float(v[i]) + b : 0.f;
-            }
-            if (p.res != nullptr) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (8 * i < ncols) {
-                  const uint4 q = r4[i];
-                  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    f[8 * i + 2 * k] += f16_lo(u[k]);
-                    f[8 * i + 2 * k + 1] += f16_hi(u[k]);
-                  }
-                }
-              }
-            }
-            __half* dst = nullptr;
-            if (pass == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                f[i] = f16_round(f[i]);      // statistics of the value as it is stored
-                ss += f[i] * f[i];
-              }
-              if (p.out != nullptr) dst = reinterpret_cast<__half*>(p.out) + off + c;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float gmm = i < ncols ? __ldg(p.norm_gamma + c + i) : 0.f;
-                const float y = f16_round(f[i]) * inv * gmm;
-                f[i] = y / (1.f + __expf(-y));
-              }
-              dst = p.norm_out + off + c;
-            }
-            if (dst != nullptr) {
-              uint4* o4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (8 * i < ncols) {
-                  uint4 q;
-                  q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
-                  q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
-                  q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
-                  q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
-                  o4[i] = q;
-                }
-              }
-            }
-          }
-        }
-      } else
-      for (int c = 0; c < p.BN; c += 32) {   // BN multiple of 16: last chunk may be half valid
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c, v);
-        tc_wait_ld();
-        const int ncols = min(32, p.BN - c);
-        if (ok) {
-          if (p.out_mode == 0) {
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float b = (p.bias != nullptr && i < ncols && n0 + c + i < p.Cout) ? __ldg(p.bias + n0 + c + i) : 0.f;
-              f[i] = __uint_as_float(v[i]) + b;
-            }
-            __half* o = reinterpret_cast<__half*>(p.out) + off + nb + c;
-            if (p.res != nullptr) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + nb + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (8 * i < ncols) {
-                  const uint4 q = r4[i];
-                  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    f[8 * i + 2 * k] += f16_lo(u[k]);
-                    f[8 * i + 2 * k + 1] += f16_hi(u[k]);
-                  }
-                }
-              }
-            }
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (8 * i < ncols) {
-                uint4 q;
-                q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
-                q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
-                q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
-                q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
-                o4[i] = q;
-              }
-            }
-          } else {
-            // head conv: fp32 channel-first video, clamp(-1, 1)                       vae.py:660-661
-            float* o = reinterpret_cast<float*>(p.out);
-            const int64_t plane = p.os_t > 0 ? p.os_t : static_cast<int64_t>(p.T) * p.H * p.W;   // channel stride
-            const int64_t pos = p.o_base + (static_cast<int64_t>(t) * p.H + h) * p.W + w;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (c == 0 && i < p.cout_real) {
-                float b = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
-                float y = __uint_as_float(v[i]) + b;
-                y = fminf(1.f, fmaxf(-1.f, y));
-                o[i * plane + pos] = y;
-              }
-            }
-          }
-        }
-      }
+      conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -340,6 +349,209 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================================
+// conv_igemm_pair_kernel — the same implicit GEMM restructured around its real limit.  ncu of the kernel above
+// (profiles/r02_ncu_vae_conv.txt): every (tap, channel block) re-fetches its 128-voxel A box and its weight slab from
+// L2 — 104 B per tensor-pipe clock per SM for Cout = 192, 146 B/clk for Cout = 96 — and the L2 -> SM path delivers
+// ~14 TB/s (51 % of its peak, latency-bound with ~200 KB in flight per SM): tensor pipe 60 % / 29 % active.
+// Here the bytes per FLOP are cut 3-4x:
+//   * a CTA owns NT vertically stacked 8 x 16 voxel tiles and loads, per (channel block, dt, dw), ONE box of
+//     (8 NT + 2) x 16 voxels; the three vertical taps dh = -1, 0, +1 of all NT tiles are row-offset views of that box
+//     (16 rows = whole swizzle atoms, so a view is just a descriptor start address) — 2.4-2.9x fewer A bytes;
+//   * two CTAs (a cluster on one TPC) issue ONE tcgen05.mma.cta_group::2 over M = 256 = tile j of both CTAs; each CTA
+//     stages HALF of the weight slab, and a slab serves all NT tile pairs — 2 NT x fewer B bytes per voxel.
+// One pipeline stage = one A box + the (<= 3) weight slabs of its vertical taps = 3 x NT x BK/16 MMAs (24 for the
+// decoder's heavy stages).  Accumulators: NT x BN columns per buffer; two buffers when they fit in 512 TMEM columns,
+// otherwise one buffer released tile by tile so the next super-tile's MMAs follow the epilogue.
+//   warp 0: TMA producer (both CTAs)   warp 1: MMA issuer (leader)   warps 2-9: two epilogue warp sets (tiles j = 0, 2 /
+//   1, 3 ...), each thread one voxel row of its tile (conv_epilogue_tile above).
+// ================================================================================================================
+constexpr int kConv2Threads = 320;
+constexpr int kDefaultConvPair = 0;   // flipped to 1 once validated and measured on the GPU (profiles/)
+constexpr int kConv2MaxGroups = 9;
+constexpr int kConv2MaxStages = 6;
+constexpr uint32_t kConv2RingBytes = 216 * 1024;
+constexpr uint32_t kConv2Smem = kConv2RingBytes + 1024 + 512;
+
+struct Conv2Params {
+  ConvParams c;
+  int ngroups;                              // distinct (dt, dw) pairs of the tap set
+  int8_t g_dt[kConv2MaxGroups], g_dw[kConv2MaxGroups], g_ntap[kConv2MaxGroups];
+  int8_t g_tap[kConv2MaxGroups][3];         // index of the tap in the packed weight matrix
+  int8_t g_dhoff[kConv2MaxGroups][3];       // dh - dh_min: row-group offset of the tap's view inside the A box
+  int dh_min, box_h;                        // A box: h from (tile origin + dh_min), box_h = 8 NT + dh_max - dh_min rows
+  uint32_t a_box_bytes, b_slab_bytes, stage_bytes;   // 1024-aligned
+  int stages, nbuf;
+  int sup_h, sup_w, num_super;              // super-tiles (pair = 16 NT x 16 voxels) per frame in h / w; total incl. t, n
+};
+
+template <int BK, int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv2Threads, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const Conv2Params q) {
+  using Cfg = ConvCfg<BK>;
+  const ConvParams& p = q.c;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConv2RingBytes);
+  uint64_t* full = bars;                                  // leader only
+  uint64_t* empty = bars + kConv2MaxStages;               // both CTAs (multicast commit)
+  uint64_t* tfull = bars + 2 * kConv2MaxStages;           // [nbuf], both CTAs (multicast commit)
+  uint64_t* tempty = bars + 2 * kConv2MaxStages + 2;      // [nbuf][NT], leader only: 4 warps x 2 CTAs arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConv2MaxStages + 2 + 2 * NT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int nstages = q.stages;
+  const int nbuf = q.nbuf;
+  const int half_n = p.BN >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < nstages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(&tfull[i], 1);
+    for (int i = 0; i < 2 * NT; ++i) mbar_init(&tempty[i], 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int steps_per_super = p.kblocks_per_tap * q.ngroups;
+
+  // super-tile -> (n block fastest, then w, h, t)
+  auto decode = [&](int st, int& n_blk, int& t, int& h0, int& w0) {
+    n_blk = st % p.num_n;
+    int r = st / p.num_n;
+    w0 = (r % q.sup_w) * kConvTW;
+    r /= q.sup_w;
+    h0 = (r % q.sup_h) * (2 * NT * kConvTH) + static_cast<int>(rank) * (NT * kConvTH);   // this CTA's first row
+    t = r / q.sup_h;
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = pair_id; st < q.num_super; st += num_pairs) {
+      int n_blk, t, h0, w0;
+      decode(st, n_blk, t, h0, w0);
+      for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+        for (int g = 0; g < q.ngroups; ++g) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            const int ntap = q.g_ntap[g];
+            uint8_t* base = smem + stage * q.stage_bytes;
+            if (leader) mbar_expect_tx(&full[stage], 2u * (static_cast<uint32_t>(q.box_h) * kConvTW * Cfg::kRowBytes +
+                                                           static_cast<uint32_t>(ntap) * half_n * Cfg::kRowBytes));
+            tma_load_4d_pair(base, &tmA, &full[stage], cb * BK, w0 + q.g_dw[g], h0 + q.dh_min,
+                             t + p.t_off + q.g_dt[g]);
+            for (int i = 0; i < ntap; ++i)
+              tma_load_2d_pair(base + q.a_box_bytes + i * q.b_slab_bytes, &tmB, &full[stage],
+                               q.g_tap[g][i] * p.Cin + cb * BK, n_blk * p.BN + static_cast<int>(rank) * half_n);
+          }
+          __syncwarp();
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA) ------------------------------
+    if (leader) {
+      const uint32_t idesc = make_idesc_f16(2 * kConvBM, static_cast<uint32_t>(p.BN), 0, 0);
+      const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, Cfg::kSBO, Cfg::kLayout);
+      constexpr uint32_t kRowGroupBytes = kConvTW * Cfg::kRowBytes;   // one h row of the box = 16 voxels
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int st = pair_id; st < q.num_super; st += num_pairs, ++it) {
+        const int buf = it % nbuf;
+        const uint32_t use = static_cast<uint32_t>(it / nbuf);
+        uint32_t started = 0;    // bit j: tile j has received its first MMA of this super-tile
+        for (int step = 0; step < steps_per_super; ++step) {
+          const int g = step % q.ngroups;
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const int ntap = q.g_ntap[g];
+          const uint32_t sbase = static_cast<uint32_t>(stage) * q.stage_bytes;
+#pragma unroll 1
+          for (int j = 0; j < NT; ++j) {
+            if (!((started >> j) & 1u)) {
+              // the accumulator of tile j must have been drained by the epilogue of its previous use
+              mbar_wait(&tempty[buf * NT + j], (use & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * NT + j) * p.BN);
+              for (int i = 0; i < ntap; ++i) {
+                const uint64_t adesc = desc0 + ((sbase + static_cast<uint32_t>(j * kConvTH + q.g_dhoff[g][i]) * kRowGroupBytes) >> 4);
+                const uint64_t bdesc = desc0 + ((sbase + q.a_box_bytes + static_cast<uint32_t>(i) * q.b_slab_bytes) >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                               (((started >> j) & 1u) | static_cast<uint32_t>(i | k)) != 0 ? 1u : 0u);
+              }
+            }
+            __syncwarp();
+            started |= 1u << j;
+          }
+          if (elect_one()) {
+            umma_commit_pair(&empty[stage], 3);
+            if (step == steps_per_super - 1) umma_commit_pair(&tfull[buf], 3);
+          }
+          __syncwarp();
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue: two warp sets, tiles j = set, set + 2, ... ------------------------------
+    const int wset = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    int it = 0;
+    for (int st = pair_id; st < q.num_super; st += num_pairs, ++it) {
+      const int buf = it % nbuf;
+      const uint32_t use = static_cast<uint32_t>(it / nbuf);
+      int n_blk, t, h0, w0;
+      decode(st, n_blk, t, h0, w0);
+      mbar_wait(&tfull[buf], use & 1u);
+      tc_fence_after();
+      for (int j = wset; j < NT; j += 2) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((buf * NT + j) * p.BN);
+        conv_epilogue_tile(p, taddr, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty[buf * NT + j], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -504,9 +716,44 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return MV_OK;
 }
 
+template <int BK, int NT>
+static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv2Params& q, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kConv2Smem)));
+    attr_set = true;
+  }
+  int pairs = sm_count() / 2;
+  if (q.num_super < pairs) pairs = q.num_super;
+  conv_igemm_pair_kernel<BK, NT><<<2 * pairs, kConv2Threads, kConv2Smem, st>>>(tmA, tmB, q);
+  MV_CHECK_LAUNCH("conv_igemm_pair_kernel");
+  return MV_OK;
+}
+
 }  // namespace mv
 
 using namespace mv;
+
+namespace {
+int g_conv_pair = -1;   // -1: read MV_CONV_PAIR on first use
+int g_conv_nt = -1;     // -1: read MV_CONV_NT on first use; 0 = automatic
+bool conv_pair_enabled() {
+  if (g_conv_pair < 0) {
+    const char* e = getenv("MV_CONV_PAIR");
+    g_conv_pair = (e != nullptr && e[0] != 0) ? (atoi(e) != 0 ? 1 : 0) : kDefaultConvPair;
+  }
+  return g_conv_pair == 1;
+}
+}  // namespace
+
+extern "C" int mv_vae_conv_config(int pair, int tiles_per_cta) {
+  if (pair >= 0) g_conv_pair = pair != 0 ? 1 : 0;
+  else if (pair == -2) g_conv_pair = -1;   // back to MV_CONV_PAIR / the built-in default
+  if (tiles_per_cta >= 0) g_conv_nt = tiles_per_cta;
+  else if (tiles_per_cta == -2) g_conv_nt = -1;
+  return MV_OK;
+}
 
 static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
                          const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
@@ -537,6 +784,103 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   MV_REQUIRE(norm_out == nullptr || (BN == Cout && out_mode == 0 && nsplit == 0),
              "mv_vae_conv_fused: the fused norm needs the whole channel row in one N tile (Cout=%d <= 256)", Cout);
   MV_REQUIRE(out != nullptr || norm_out != nullptr, "mv_vae_conv: no output");
+
+  // ---- CTA-pair kernel (conv_igemm_pair_kernel) for the tensor-bound convolutions -----------------------------------
+  if (conv_pair_enabled() && (BK == 64 || BK == 32) && BN % 16 == 0 && ntaps >= 2) {
+    Conv2Params q;
+    memset(&q, 0, sizeof(q));
+    bool ok = true;
+    int dh_min = 127, dh_max = -127;
+    for (int i = 0; i < ntaps; ++i) {
+      const int dt = taps_dt_dh_dw[3 * i], dh = taps_dt_dh_dw[3 * i + 1], dw = taps_dt_dh_dw[3 * i + 2];
+      dh_min = dh < dh_min ? dh : dh_min;
+      dh_max = dh > dh_max ? dh : dh_max;
+      int g = 0;
+      while (g < q.ngroups && !(q.g_dt[g] == dt && q.g_dw[g] == dw)) ++g;
+      if (g == q.ngroups) {
+        if (q.ngroups == kConv2MaxGroups) { ok = false; break; }
+        q.g_dt[g] = static_cast<int8_t>(dt);
+        q.g_dw[g] = static_cast<int8_t>(dw);
+        q.g_ntap[g] = 0;
+        ++q.ngroups;
+      }
+      if (q.g_ntap[g] == 3) { ok = false; break; }
+      q.g_tap[g][q.g_ntap[g]] = static_cast<int8_t>(i);
+      q.g_dhoff[g][q.g_ntap[g]] = static_cast<int8_t>(dh);     // rebased below
+      ++q.g_ntap[g];
+    }
+    if (ok && dh_max - dh_min <= 2) {
+      for (int g = 0; g < q.ngroups; ++g)
+        for (int i = 0; i < q.g_ntap[g]; ++i) q.g_dhoff[g][i] = static_cast<int8_t>(q.g_dhoff[g][i] - dh_min);
+      int nt = (BK == 64) ? 2 : ((BN <= 128) ? 4 : 2);
+      if (g_conv_nt < 0) {             // MV_CONV_NT=1|2|4 / mv_vae_conv_config: tiles per CTA (A/B measurements)
+        const char* e = getenv("MV_CONV_NT");
+        g_conv_nt = e ? atoi(e) : 0;
+      }
+      if (g_conv_nt == 1 || g_conv_nt == 2 || g_conv_nt == 4) nt = g_conv_nt;
+      while (nt > 1 && nt * BN > 512) nt >>= 1;
+      if (BK == 64 && nt == 4) nt = 2;                 // instantiated: (64, 1|2), (32, 1|2|4)
+      const uint32_t rowb = static_cast<uint32_t>(BK) * 2;
+      q.dh_min = dh_min;
+      q.box_h = 8 * nt + (dh_max - dh_min);
+      q.a_box_bytes = (static_cast<uint32_t>(q.box_h) * kConvTW * rowb + 1023u) & ~1023u;
+      q.b_slab_bytes = (static_cast<uint32_t>(BN / 2) * rowb + 1023u) & ~1023u;
+      q.stage_bytes = q.a_box_bytes + 3 * q.b_slab_bytes;
+      q.stages = static_cast<int>(kConv2RingBytes / q.stage_bytes);
+      if (q.stages > kConv2MaxStages) q.stages = kConv2MaxStages;
+      q.nbuf = (2 * nt * BN <= 512) ? 2 : 1;
+      q.sup_h = (out_H + 2 * nt * kConvTH - 1) / (2 * nt * kConvTH);
+      q.sup_w = (out_W + kConvTW - 1) / kConvTW;
+      const int num_n = Cout / BN;
+      const int64_t ns = static_cast<int64_t>(num_n) * q.sup_h * q.sup_w * out_T;
+      if (q.stages >= 2 && ns < (1ll << 31) && q.box_h <= 256) {
+        q.num_super = static_cast<int>(ns);
+        ConvParams& p = q.c;
+        p.bias = bias;
+        p.res = reinterpret_cast<const __half*>(res_cl);
+        p.out = out;
+        p.o_base = o_base;
+        p.os_t = os_t;
+        p.os_h = os_h;
+        p.os_w = os_w;
+        p.nsplit = nsplit;
+        p.nsplit_off = nsplit_off;
+        p.T = out_T;
+        p.t_off = t_off;
+        p.H = out_H;
+        p.W = out_W;
+        p.Cin = Cin;
+        p.Cout = Cout;
+        p.BN = BN;
+        p.ntaps = ntaps;
+        p.num_n = num_n;
+        p.kblocks_per_tap = Cin / BK;
+        p.out_mode = out_mode;
+        p.cout_real = cout_real;
+        p.norm_gamma = norm_gamma;
+        p.norm_out = reinterpret_cast<__half*>(norm_out);
+        CUtensorMap tmA2, tmB2;
+        {
+          uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
+          uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)Cin * in_W * 2, (uint64_t)Cin * in_W * in_H * 2};
+          uint32_t box[4] = {(uint32_t)BK, kConvTW, (uint32_t)q.box_h, 1};
+          rc = make_tmap_bf16_sw(&tmA2, in_cl, 4, dims, str, box, BK * 2);
+          if (rc != MV_OK) return rc;
+        }
+        {
+          uint64_t dims[2] = {(uint64_t)ntaps * Cin, (uint64_t)Cout};
+          uint64_t str[2] = {2, (uint64_t)ntaps * Cin * 2};
+          uint32_t box[2] = {(uint32_t)BK, (uint32_t)(BN / 2)};
+          rc = make_tmap_bf16_sw(&tmB2, w_packed, 2, dims, str, box, BK * 2);
+          if (rc != MV_OK) return rc;
+        }
+        cudaStream_t st2 = static_cast<cudaStream_t>(stream);
+        if (BK == 64) return nt == 2 ? launch_conv_pair<64, 2>(tmA2, tmB2, q, st2) : launch_conv_pair<64, 1>(tmA2, tmB2, q, st2);
+        if (nt == 4) return launch_conv_pair<32, 4>(tmA2, tmB2, q, st2);
+        return nt == 2 ? launch_conv_pair<32, 2>(tmA2, tmB2, q, st2) : launch_conv_pair<32, 1>(tmA2, tmB2, q, st2);
+      }
+    }
+  }
 
   CUtensorMap tmA, tmB;
   {

@@ -207,7 +207,7 @@ def test_gemm_cta_pair(mv, M, N, K, epi):
             mv.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), out, epi)
         torch.cuda.synchronize()
     finally:
-        mv.gemm_config(0)
+        mv.gemm_config(-2)
     assert torch.isfinite(out.float()).all()
     assert rel_l2(out.float(), ref) <= 3e-3
     err = (out.float().cpu() - ref).abs()
@@ -231,7 +231,7 @@ def test_gemm_cta_pair_ksplit_equals_single_cta(mv):
             mv.gemm_ksplit(a, w, bias, o, 0)
             torch.cuda.synchronize()
         finally:
-            mv.gemm_config(0)
+            mv.gemm_config(-2)
         outs.append(o)
     ref = O.bf16_rt(a.permute(1, 0, 2).reshape(M, P * Kb).float().cpu() @ w.float().cpu().t() + bias.cpu())
     assert rel_l2(outs[1].float(), ref) <= 3e-3

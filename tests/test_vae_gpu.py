@@ -32,8 +32,18 @@ def vae():
     return m.to(DEV), g
 
 
+@pytest.fixture(params=[0, 1], ids=["conv1cta", "convpair"])
+def conv_kernel(request):
+    """Both convolution kernels: the single-CTA implicit GEMM and the CTA-pair one (cta_group::2, stacked tiles, one A box
+    per (dt, dw)); the product default is whichever measured faster (csrc/vae_conv_sm100.cu::kDefaultConvPair)."""
+    import movii_b200 as mv
+    mv.vae_conv_config(request.param)
+    yield request.param
+    mv.vae_conv_config(-2, -2)
+
+
 @pytest.mark.parametrize("case", [(1, 4, 6), (2, 5, 9), (3, 4, 6), (5, 4, 4)])
-def test_vae_decode_matches_reference_golden(vae, case):
+def test_vae_decode_matches_reference_golden(vae, case, conv_kernel):
     m, g = vae
     rec = g["cases"][case]
     y = m.decode(rec["z"][None].to(DEV))[0].cpu()
@@ -50,7 +60,7 @@ def test_vae_decode_matches_reference_golden(vae, case):
 
 
 @pytest.mark.parametrize("case", [(5, 4, 4), (3, 4, 6)])
-def test_vae_temporal_chunking_is_exact(vae, case):
+def test_vae_temporal_chunking_is_exact(vae, case, conv_kernel):
     """The decode runs in temporal chunks with a two-frame feature cache per temporal conv (the reference's scheme,
     vae.py:28-36,205-217, with larger chunks).  Any chunk size must give the SAME BITS as the whole-sequence pass:
     same taps, same accumulation order, only the provenance of the two history frames differs — including chunk 1
@@ -71,7 +81,7 @@ def test_vae_temporal_chunking_is_exact(vae, case):
     assert (whole.cpu() - rec["y"].float()).abs().max().item() <= 1e-2
 
 
-def test_vae_conv_primitives(vae):
+def test_vae_conv_primitives(vae, conv_kernel):
     """One 3x3x3 causal conv and one sub-pixel upsample conv against torch, ragged grid."""
     import torch.nn.functional as F
     import movii_b200 as mv
@@ -99,3 +109,52 @@ def test_vae_conv_primitives(vae):
     ref2 = F.conv2d(xf, V.f16_rt(w2), b2, padding=1).permute(0, 2, 3, 1)
     err2 = (up.float().cpu() - ref2).abs().max().item()
     assert err2 <= 6e-3, err2    # four pre-summed fp16 sub-pixel kernels vs one 3x3 kernel on the upsampled image
+
+
+@pytest.mark.parametrize("shape", [(3, 70, 40, 96, 96), (2, 33, 50, 192, 192), (2, 40, 24, 384, 384), (3, 19, 17, 96, 16),
+                                   (2, 64, 32, 384, 768)])
+@pytest.mark.parametrize("mode", ["plain", "res", "fused"])
+@pytest.mark.parametrize("nt", [0, 1, 2, 4])
+def test_vae_conv_pair_matches_single_cta(shape, mode, nt):
+    """The CTA-pair kernel vs the single-CTA kernel on the decoder's channel plans (96, 192, 384 -> 2 N blocks, the
+    16-wide padded head, the 768-wide time_conv with its channel-block split), ragged grids (H, W not multiples of the
+    super-tile), two cached frames in front (t_off = 2), with residual / with the fused RMS_norm+SiLU epilogue.
+    Same operands, same fp32 accumulation, different summation order: differences are fp16 output rounding flips."""
+    import movii_b200 as mv
+    from wan.modules.vae import _Conv, _taps
+    T, H, W, Ci, Co = shape
+    if mode == "fused" and Co > 256:
+        pytest.skip("the fused norm epilogue needs the whole channel row in one tile")
+    g = torch.Generator().manual_seed(H * W + Ci + Co)
+    x = torch.randn(T + 2, H, W, Ci, generator=g).half().to(DEV)
+    time_conv = Co == 768
+    taps = _taps(3, 1, 1) if time_conv else _taps(3, 3, 3)
+    wt = torch.randn(Co, Ci, 3, 1 if time_conv else 3, 1 if time_conv else 3, generator=g) / math.sqrt(len(taps) * Ci)
+    c = _Conv(wt, 0.1 * torch.randn(Co, generator=g), taps, DEV)
+    res = torch.randn(T, H, W, c.cout, generator=g).half().to(DEV) if mode == "res" else None
+    gamma = (1 + 0.1 * torch.randn(c.cout, generator=g)).to(DEV)
+    outs = []
+    for pair in (0, 1):
+        mv.vae_conv_config(pair, nt)          # nt: tiles per CTA of the pair kernel (0 = automatic choice)
+        try:
+            if time_conv:      # frame interleave store: channel block >= 384 goes to the next frame
+                Ch = Co // 2
+                out = torch.zeros(2 * T, H, W, Ch, dtype=torch.float16, device=DEV)
+                fe = H * W * Ch
+                mv.vae_conv(x, c, out, o_base=0, os_t=2 * fe, os_h=W * Ch, os_w=Ch, nsplit=Ch, nsplit_off=fe, t_off=2)
+            elif mode == "fused":
+                out = torch.zeros(T, H, W, c.cout, dtype=torch.float16, device=DEV)
+                raw = torch.zeros_like(out)
+                mv.vae_conv_fused(x, c, raw, gamma, out, o_base=0, os_t=H * W * c.cout, os_h=W * c.cout, os_w=c.cout, t_off=2)
+                out = torch.cat([out, raw])
+            else:
+                out = torch.zeros(T, H, W, c.cout, dtype=torch.float16, device=DEV)
+                mv.vae_conv(x, c, out, res=res, o_base=0, os_t=H * W * c.cout, os_h=W * c.cout, os_w=c.cout, t_off=2)
+            torch.cuda.synchronize()
+        finally:
+            mv.vae_conv_config(-2, -2)
+        outs.append(out.float())
+    a, b = outs
+    assert torch.isfinite(b).all()
+    assert (a - b).abs().max().item() <= 4e-3 * max(1.0, a.abs().max().item()), (a - b).abs().max().item()
+    assert ((a - b).norm() / a.norm()).item() <= 5e-4

@@ -49,7 +49,7 @@ def bench_gemm(M, N, K, epi=0):
     for pair in (0, 1):
         mv.gemm_config(pair)
         res[pair] = timeit(lambda: mv.gemm(a, w, bias, out, epi, gate=gate))
-    mv.gemm_config(-1)
+    mv.gemm_config(-2)
     ms_ref = timeit(lambda: torch.nn.functional.linear(a, w, bias.bfloat16()))
     fl = 2.0 * M * N * K
     print(json.dumps(dict(kind="gemm", M=M, N=N, K=K, epi=epi, ms=round(res[0], 4), tflops=round(fl / res[0] / 1e9, 1),

@@ -34,6 +34,9 @@ def timeit(fn, iters=3):
     return sorted(ts)[len(ts) // 2]
 
 
+ONLY = [a for a in os.environ.get("CONV_VARIANTS", "").split(",") if a]   # e.g. CONV_VARIANTS=pair_nt2 for ncu
+
+
 def main():
     which = sys.argv[1:] or ["A", "B", "C", "D", "up2"]
     mv.device_check()
@@ -50,10 +53,13 @@ def main():
             def run():
                 for (a, b), c in par.items():
                     mv.vae_conv(x, c, out, o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co, os_w=2 * Co)
-            ms = timeit(run)
             fl = 2.0 * 16 * Ci * Co * T * H * W            # 4 parities x 4 taps, as executed
-            print(json.dumps(dict(kind="vae_up2d_subpixel", shape=[T, H, W, Ci, Co], ms=round(ms, 3),
-                                  tflops_executed=round(fl / ms / 1e9, 1))), flush=True)
+            rec = dict(kind="vae_up2d_subpixel", shape=[T, H, W, Ci, Co])
+            for label, pair, nt in (("1cta", 0, 0), ("pair_nt2", 1, 2), ("pair_nt4", 1, 4)):
+                mv.vae_conv_config(pair, nt)
+                rec[label + "_tflops_executed"] = round(fl / timeit(run) / 1e9, 1)
+            mv.vae_conv_config(-2, -2)
+            print(json.dumps(rec), flush=True)
             continue
         T, H, W, Ci, Co = STAGES[st]
         x = torch.randn(T + 2, H, W, Ci, device=DEV, generator=g).half()
@@ -64,12 +70,18 @@ def main():
         gamma = torch.ones(Co, device=DEV)
         kw = dict(o_base=0, os_t=H * W * Co, os_h=W * Co, os_w=Co, t_off=2)
         fl = 2.0 * 27 * Ci * Co * T * H * W
-        ms = timeit(lambda: mv.vae_conv(x, c, out, res=res, **kw))
-        rec = dict(kind="vae_conv3x3x3", stage=st, shape=[T, H, W, Ci, Co], ms=round(ms, 3), tflops=round(fl / ms / 1e9, 1))
-        if Co <= 256:
-            nout = torch.empty_like(out)
-            ms2 = timeit(lambda: mv.vae_conv_fused(x, c, None, gamma, nout, **kw))
-            rec.update(fused_ms=round(ms2, 3), fused_tflops=round(fl / ms2 / 1e9, 1))
+        rec = dict(kind="vae_conv3x3x3", stage=st, shape=[T, H, W, Ci, Co])
+        nout = torch.empty_like(out)
+        for label, pair, nt in (("1cta", 0, 0), ("pair_nt1", 1, 1), ("pair_nt2", 1, 2), ("pair_nt4", 1, 4)):
+            if ONLY and label not in ONLY:
+                continue
+            mv.vae_conv_config(pair, nt)
+            ms = timeit(lambda: mv.vae_conv(x, c, out, res=res, **kw))
+            rec[label + "_tflops"] = round(fl / ms / 1e9, 1)
+            if Co <= 256:
+                ms2 = timeit(lambda: mv.vae_conv_fused(x, c, None, gamma, nout, **kw))
+                rec[label + "_fused_tflops"] = round(fl / ms2 / 1e9, 1)
+        mv.vae_conv_config(-2, -2)
         print(json.dumps(rec), flush=True)
         del x, out, res
 
