@@ -130,5 +130,12 @@ if __name__ == "__main__":
         bench_attn(75600, 5, None)
     if "attn_720p" in which:     # the bench.py self-attention shape (one launch; for the ncu traffic capture)
         bench_attn(75600, 40, None)
+    for w in which:              # attn_shape:Lq:Lk:H -> one launch shape (ncu traffic captures for profiles/attn_traffic.json)
+        if w.startswith("attn_shape:"):
+            _, lq, lk, h = w.split(":")
+            bench_attn(int(lq), int(h), int(lk))
+        if w.startswith("gemm_shape:"):
+            _, m, n, k, epi = w.split(":")
+            bench_gemm(int(m), int(n), int(k), int(epi))
     if "gemm_one" in which:
         bench_gemm(75600, 5120, 5120, 2)

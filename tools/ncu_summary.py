@@ -1,5 +1,6 @@
 """Summarise ncu outputs into small text files for profiles/ (the raw .ncu-rep / launch csv stay in gpurun_out/).
   python tools/ncu_summary.py rep <file.ncu-rep>            -> key metrics of each captured launch
+  python tools/ncu_summary.py compact <file.ncu-rep>        -> one line per captured launch (time, tensor %, L2->SM, DRAM)
   python tools/ncu_summary.py list <launches.csv>           -> per-kernel time shares of the profiled command"""
 import csv
 import io
@@ -34,6 +35,33 @@ def rep(path):
                 print("  %-95s %s %s" % (h, r[i], units[i]))
 
 
+def compact(path):
+    """One line per captured launch with the metrics the conv / GEMM / attention analysis uses."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    want = [("ms", "gpu__time_duration.sum"), ("sm_ghz", "sm__cycles_elapsed.avg.per_second"),
+            ("tensor_pct", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
+            ("tensor_mem_pct", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            ("l2_to_sm_GB", "l1tex__m_xbar2l1tex_read_bytes.sum"),
+            ("l2_to_sm_pct", "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed"),
+            ("lts_pct", "lts__t_sectors.sum.pct_of_peak_sustained_elapsed"), ("l2_hit_pct", "lts__t_sector_hit_rate.pct"),
+            ("dram_rd_GB", "dram__bytes_read.sum"), ("dram_wr_GB", "dram__bytes_write.sum"),
+            ("issue_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            ("regs", "launch__registers_per_thread"), ("grid", "launch__grid_size"), ("block", "launch__block_size")]
+    col = {}
+    for key, name in want:
+        for i, h in enumerate(hdr):
+            if h == name or h.endswith("." + name):
+                col[key] = i
+                break
+    name_i = hdr.index("Kernel Name")
+    print("units: " + ", ".join("%s[%s]" % (k, units[i]) for k, i in col.items()))
+    for r in rows[2:]:
+        print("%-3s %-48s " % (r[0], r[name_i].split("(")[0][-48:]) + " ".join(
+            "%s=%s" % (k, r[i][:8] if r[i] not in ("", "no data") else "-") for k, i in col.items()))
+
+
 def launch_list(path):
     tot = defaultdict(float)
     cnt = defaultdict(int)
@@ -57,4 +85,4 @@ def launch_list(path):
 
 
 if __name__ == "__main__":
-    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "list": launch_list, "compact": compact}[sys.argv[1]](sys.argv[2])
