@@ -44,6 +44,28 @@ def main():
     if tf:
         rec["tflops"] = round(tf / ms * 1e3, 1)
     print(json.dumps(rec), flush=True)
+    # where the decode goes: one more decode with every launch bracketed by CUDA events (adds launch gaps; shares only)
+    names = ["mv_vae_conv", "mv_vae_conv_fused", "mv_vae_rmsnorm_silu", "mv_gemm_f16", "mv_softmax_rows", "mv_vae_latent_in"]
+    timed = mv.time_kernels(names)
+    vae.decode([z])
+    torch.cuda.synchronize()
+    agg = {}
+    for n in names:
+        for (s_, e_, a) in timed.get(n, []):
+            if n == "mv_vae_conv":
+                key = "conv %dtap %d->%d @H%d" % (a[15], a[4], a[13], a[2])
+            elif n == "mv_vae_conv_fused":
+                key = "conv+norm %dtap %d->%d @H%d" % (a[13], a[4], a[12], a[2])
+            elif n == "mv_vae_rmsnorm_silu":
+                key = "rmsnorm_silu C%d" % a[4]
+            else:
+                key = n
+            t_, c_ = agg.get(key, (0.0, 0))
+            agg[key] = (t_ + s_.elapsed_time(e_), c_ + 1)
+    mv.time_kernels(None)
+    tot = sum(v[0] for v in agg.values())
+    print(json.dumps(dict(breakdown_ms={k: [round(v[0], 1), v[1]] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+                          sum_ms=round(tot, 1))), flush=True)
 
 
 if __name__ == "__main__":
