@@ -452,7 +452,7 @@ constexpr uint32_t kKVTileBytes2 = kBKV2 * kD * 2;     // 32 KB
 constexpr uint32_t kKVHalfBytes2 = kKVTileBytes2 / 2;  // [128 x 64] sub-tile
 constexpr uint32_t kAttnSmem2 = 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 1024 + 512;
 
-template <int EMU, bool PP, bool TRACE, bool STALE>
+template <int EMU, bool PP, bool TRACE, bool STALE, bool HI = false>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -469,7 +469,10 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* o_done = p_full + 2;              // [w] -> 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // HI: the role warps (TMA producer, the two MMA issuers) are physical warps 8-11, the softmax warpgroups 0-7: the
+  // sub-partition arbiter favours the highest warp id, so a pending tcgen05.mma / TMA issue never queues behind the
+  // softmax instruction stream sharing its sub-partition (the shift is a multiple of 4: TMEM quadrants are unchanged)
+  const int warp = HI ? ((threadIdx.x >> 5) + 4) % 12 : (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int q0 = blockIdx.x * (2 * kBQ);
@@ -1007,6 +1010,8 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem2)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1015,6 +1020,7 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     if (stale && !p.pingpong && emu <= 1 && softmax_scale > 0.f) {
       if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else if (emu == 1) attention_fwd_k128_kernel<1, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+      else if (roles_hi()) attention_fwd_k128_kernel<0, false, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else attention_fwd_k128_kernel<0, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
     } else
     if (p.trace != nullptr && p.pingpong) attention_fwd_k128_kernel<0, true, true, false><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);

@@ -173,7 +173,7 @@ __device__ __forceinline__ void epi_drain_tile(const GemmParams& p, uint32_t tad
   }
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool HI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -193,7 +193,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int pw = threadIdx.x >> 5;                      // physical warp: TMEM lane quadrant = pw & 3
+  const int warp = HI ? (pw + 2) % 6 : pw;              // role id: 0 TMA, 1 MMA, 2-5 epilogue (HI: roles on warps 4, 5)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -283,7 +284,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------ epilogue ----------------------------------
     // TMEM -> registers (one accumulator row per thread) -> per-warp smem transpose -> global, so that every
     // global access of a warp covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = pw & 3;  // TMEM lane quadrant this warp may access
     uint8_t* stg = sEpi + quad * 4096;  // 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
     int as = 0;
     uint32_t aphase = 0;
@@ -331,7 +332,7 @@ constexpr uint32_t kPairBBytes = (kPairBN / 2) * BK * 2;   // 16 KB
 constexpr uint32_t kPairStageBytes = kABytes + kPairBBytes;
 constexpr uint32_t kPairSmem = kPairStages * kPairStageBytes + kEpiStageBytes + 1024 + 256;
 
-template <int EPI>
+template <int EPI, bool HI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const GemmParams p) {
@@ -347,7 +348,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tempty = bars + 2 * kPairStages + 2;  // used in the leader only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int pw = threadIdx.x >> 5;                      // physical warp: TMEM lane quadrant = pw & 3
+  const int warp = HI ? (pw + 2) % 6 : pw;              // role id: 0 TMA, 1 MMA, 2-5 epilogue (HI: roles on warps 4, 5)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -441,7 +443,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ----------------------------------
-    const int quad = warp & 3;
+    const int quad = pw & 3;
     uint8_t* stg = sEpi + quad * 4096;
     int as = 0;
     uint32_t aphase = 0;
@@ -474,13 +476,16 @@ template <int EPI>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kPairSmem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kPairSmem)));
     attr_set = true;
   }
   int pairs = sm_count() / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  gemm_bf16_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmem, st>>>(tmA, tmB, p);
+  if (roles_hi()) gemm_bf16_pair_kernel<EPI, true><<<2 * pairs, kGemmThreads, kPairSmem, st>>>(tmA, tmB, p);
+  else gemm_bf16_pair_kernel<EPI, false><<<2 * pairs, kGemmThreads, kPairSmem, st>>>(tmA, tmB, p);
   MV_CHECK_LAUNCH("gemm_bf16_pair_kernel");
   return MV_OK;
 }
@@ -500,12 +505,15 @@ template <int EPI, int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GemmCfg<BN>::kSmem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<BN>::kSmem)));
     attr_set = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  gemm_bf16_kernel<EPI, BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(tmA, tmB, p);
+  if (roles_hi()) gemm_bf16_kernel<EPI, BN, true><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(tmA, tmB, p);
+  else gemm_bf16_kernel<EPI, BN, false><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(tmA, tmB, p);
   MV_CHECK_LAUNCH("gemm_bf16_kernel");
   return MV_OK;
 }

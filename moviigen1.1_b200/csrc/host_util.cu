@@ -1,5 +1,6 @@
 #include "host_util.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace mv {
@@ -39,6 +40,17 @@ int require_sm100() {
   }
   return cached_rc;
 }
+
+static int g_roles_hi = -1;
+constexpr int kDefaultRolesHi = 0;
+bool roles_hi() {
+  if (g_roles_hi < 0) {
+    const char* e = getenv("MV_ROLES_HI");
+    g_roles_hi = (e != nullptr && e[0] != 0) ? (atoi(e) != 0 ? 1 : 0) : kDefaultRolesHi;
+  }
+  return g_roles_hi == 1;
+}
+void set_roles_hi(int v) { g_roles_hi = v; }
 
 int sm_count() {
   static thread_local int cached_dev = -1;
@@ -131,3 +143,8 @@ int make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64
 extern "C" const char* mv_last_error(void) { return mv::g_err; }
 extern "C" int mv_version(void) { return 100; }
 extern "C" int mv_device_check(void) { return mv::require_sm100(); }
+extern "C" int mv_roles_config(int hi) {
+  if (hi >= 0) mv::set_roles_hi(hi != 0 ? 1 : 0);
+  else if (hi == -2) mv::set_roles_hi(-1);
+  return MV_OK;
+}

@@ -16,6 +16,11 @@ int cuda_fail(cudaError_t e, const char* what);
 // MV_OK if the current device is CC 10.x; caches the answer per device.
 int require_sm100();
 int sm_count();
+// 1: role warps (TMA producer, MMA issuer) sit at the HIGHEST warp ids of the CTA — the SM sub-partition arbiter favours
+// the highest warp id, so a pending TMA / tcgen05.mma issue is not queued behind the epilogue / softmax instruction
+// streams that share its sub-partition.  MV_ROLES_HI / mv_roles_config(); default = the measured winner.
+bool roles_hi();
+void set_roles_hi(int v);
 
 // Encodes a tiled bf16 tensor map.  dims/strides innermost first; strides in BYTES for dims 1..rank-1
 // (dim 0 is contiguous).  Swizzle 128B requires box[0] * 2 bytes == 128.

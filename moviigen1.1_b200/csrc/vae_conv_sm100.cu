@@ -67,6 +67,104 @@ struct ConvCfg {
   static constexpr uint32_t kABytes = kConvBM * kRowBytes;
 };
 
+// Fused RMS_norm + SiLU of the output row (vae.py:39-54,194-199): the whole channel row of this voxel sits in this
+// thread's TMEM lane, so the consumer's normalised input is produced here and the stand-alone normalisation pass
+// over HBM disappears.  Pass 1: bias / residual, sum of squares of the value AS STORED (fp16-rounded), optional raw
+// store; pass 2: re-read TMEM, normalise, SiLU, store.  FULL: BN is a multiple of 32 (every chunk has 32 columns):
+// vector loads of bias / gamma, no per-element predicates.
+template <bool FULL>
+__device__ __forceinline__ void conv_epilogue_fused(const ConvParams& p, uint32_t taddr, int64_t off, bool ok) {
+  float ss = 0.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const float inv = pass == 0 ? 0.f : sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 1
+    for (int c = 0; c < p.BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_x32(taddr + c, v);
+      tc_wait_ld();
+      const int ncols = FULL ? 32 : min(32, p.BN - c);
+      if (!ok) continue;
+      float f[32];
+      if (FULL && p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + i);
+          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float b = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + c + i) : 0.f;
+          f[i] = i < ncols ? __uint_as_float(v[i]) + b : 0.f;
+        }
+      }
+      if (p.res != nullptr) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (8 * i < ncols) {
+            const uint4 q = r4[i];
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f[8 * i + 2 * k] += f16_lo(u[k]);
+              f[8 * i + 2 * k + 1] += f16_hi(u[k]);
+            }
+          }
+        }
+      }
+      __half* dst = nullptr;
+      if (pass == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          f[i] = f16_round(f[i]);      // statistics of the value as it is stored
+          ss += f[i] * f[i];
+        }
+        if (p.out != nullptr) dst = reinterpret_cast<__half*>(p.out) + off + c;
+      } else {
+        if (FULL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.norm_gamma + c) + i);
+            const float gg[4] = {g4.x * inv, g4.y * inv, g4.z * inv, g4.w * inv};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float y = f16_round(f[4 * i + k]) * gg[k];
+              f[4 * i + k] = __fdividef(y, 1.f + __expf(-y));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float gmm = i < ncols ? __ldg(p.norm_gamma + c + i) : 0.f;
+            const float y = f16_round(f[i]) * (gmm * inv);
+            f[i] = __fdividef(y, 1.f + __expf(-y));
+          }
+        }
+        dst = p.norm_out + off + c;
+      }
+      if (dst != nullptr) {
+        uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (8 * i < ncols) {
+            uint4 q;
+            q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
+            q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
+            q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
+            q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
+            o4[i] = q;
+          }
+        }
+      }
+    }
+  }
+}
+
 // Epilogue of one accumulator tile for ONE output voxel (t, h, w) = this thread's TMEM lane: bias, residual, store —
 // or, with norm_out, the consumer's RMS_norm + SiLU fused in (two passes over the TMEM row).  taddr = this warp's lane
 // quadrant + the tile's first accumulator column.
@@ -80,75 +178,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
     off += p.nsplit_off;
   }
   if (p.norm_out != nullptr) {
-    // Fused RMS_norm + SiLU of the output row (vae.py:39-54,194-199): the whole channel row of this voxel sits in
-    // this thread's TMEM lane, so the consumer's normalised input is produced here and the stand-alone
-    // normalisation pass over HBM disappears.  Pass 1: bias/residual, sum of squares, (optional) raw store;
-    // pass 2: re-read TMEM, normalise, SiLU, store.
-    float ss = 0.f;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const float inv = pass == 0 ? 0.f : sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll 1
-      for (int c = 0; c < p.BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c, v);
-        tc_wait_ld();
-        const int ncols = min(32, p.BN - c);
-        if (!ok) continue;
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float b = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + c + i) : 0.f;
-          f[i] = i < ncols ? __uint_as_float(v[i]) + b : 0.f;
-        }
-        if (p.res != nullptr) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off + c);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (8 * i < ncols) {
-              const uint4 q = r4[i];
-              const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                f[8 * i + 2 * k] += f16_lo(u[k]);
-                f[8 * i + 2 * k + 1] += f16_hi(u[k]);
-              }
-            }
-          }
-        }
-        __half* dst = nullptr;
-        if (pass == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            f[i] = f16_round(f[i]);      // statistics of the value as it is stored
-            ss += f[i] * f[i];
-          }
-          if (p.out != nullptr) dst = reinterpret_cast<__half*>(p.out) + off + c;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float gmm = i < ncols ? __ldg(p.norm_gamma + c + i) : 0.f;
-            const float y = f16_round(f[i]) * inv * gmm;
-            f[i] = y / (1.f + __expf(-y));
-          }
-          dst = p.norm_out + off + c;
-        }
-        if (dst != nullptr) {
-          uint4* o4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (8 * i < ncols) {
-              uint4 q;
-              q.x = pack_f16(f[8 * i + 0], f[8 * i + 1]);
-              q.y = pack_f16(f[8 * i + 2], f[8 * i + 3]);
-              q.z = pack_f16(f[8 * i + 4], f[8 * i + 5]);
-              q.w = pack_f16(f[8 * i + 6], f[8 * i + 7]);
-              o4[i] = q;
-            }
-          }
-        }
-      }
-    }
+    if ((p.BN & 31) == 0) conv_epilogue_fused<true>(p, taddr, off, ok);
+    else conv_epilogue_fused<false>(p, taddr, off, ok);
   } else
   for (int c = 0; c < p.BN; c += 32) {   // BN multiple of 16: last chunk may be half valid
     uint32_t v[32];
@@ -210,7 +241,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
   }
 }
 
-template <int BK>
+template <int BK, bool HI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvParams p) {
@@ -228,7 +259,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty = bars + 2 * kConvMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConvMaxStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int pw = threadIdx.x >> 5;                      // physical warp: TMEM lane quadrant = pw & 3
+  const int warp = HI ? (pw + 2) % 6 : pw;              // role id: 0 TMA, 1 MMA, 2-5 epilogue (HI: roles on warps 4, 5)
   const int lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * Cfg::kRowBytes;
 
@@ -325,7 +357,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (as == 0) aphase ^= 1;
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = pw & 3;
     int as = 0;
     uint32_t aphase = 0;
     const int r = quad * 32 + lane;
@@ -388,7 +420,7 @@ struct Conv2Params {
   int sup_h, sup_w, num_super;              // super-tiles (pair = 16 NT x 16 voxels) per frame in h / w; total incl. t, n
 };
 
-template <int BK, int NT>
+template <int BK, int NT, bool HI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv2Threads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const Conv2Params q) {
@@ -403,7 +435,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tempty = bars + 2 * kConv2MaxStages + 2;      // [nbuf][NT], leader only: 4 warps x 2 CTAs arrive
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConv2MaxStages + 2 + 2 * NT);
 
-  const int warp = threadIdx.x >> 5;
+  const int pw = threadIdx.x >> 5;                      // physical warp: TMEM lane quadrant = pw & 3
+  const int warp = HI ? (pw + 2) % 10 : pw;             // role id: 0 TMA, 1 MMA, 2-9 epilogue (HI: roles on warps 8, 9)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -526,7 +559,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else {
     // ------------------------------ epilogue: two warp sets, tiles j = set, set + 2, ... ------------------------------
     const int wset = (warp - 2) >> 2;
-    const int quad = warp & 3;
+    const int quad = pw & 3;
     const int r = quad * 32 + lane;
     int it = 0;
     for (int st = pair_id; st < q.num_super; st += num_pairs, ++it) {
@@ -706,12 +739,15 @@ template <int BK>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kConvSmem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kConvSmem)));
     attr_set = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_igemm_kernel<BK><<<grid, kConvThreads, kConvSmem, st>>>(tmA, tmB, p);
+  if (roles_hi()) conv_igemm_kernel<BK, true><<<grid, kConvThreads, kConvSmem, st>>>(tmA, tmB, p);
+  else conv_igemm_kernel<BK, false><<<grid, kConvThreads, kConvSmem, st>>>(tmA, tmB, p);
   MV_CHECK_LAUNCH("conv_igemm_kernel");
   return MV_OK;
 }
@@ -720,13 +756,16 @@ template <int BK, int NT>
 static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv2Params& q, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BK, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kConv2Smem)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BK, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kConv2Smem)));
     attr_set = true;
   }
   int pairs = sm_count() / 2;
   if (q.num_super < pairs) pairs = q.num_super;
-  conv_igemm_pair_kernel<BK, NT><<<2 * pairs, kConv2Threads, kConv2Smem, st>>>(tmA, tmB, q);
+  if (roles_hi()) conv_igemm_pair_kernel<BK, NT, true><<<2 * pairs, kConv2Threads, kConv2Smem, st>>>(tmA, tmB, q);
+  else conv_igemm_pair_kernel<BK, NT, false><<<2 * pairs, kConv2Threads, kConv2Smem, st>>>(tmA, tmB, q);
   MV_CHECK_LAUNCH("conv_igemm_pair_kernel");
   return MV_OK;
 }
@@ -812,7 +851,10 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
     if (ok && dh_max - dh_min <= 2) {
       for (int g = 0; g < q.ngroups; ++g)
         for (int i = 0; i < q.g_ntap[g]; ++i) q.g_dhoff[g][i] = static_cast<int8_t>(q.g_dhoff[g][i] - dh_min);
-      int nt = (BK == 64) ? 2 : ((BN <= 128) ? 4 : 2);
+      // tiles per CTA: measured (profiles/r02_vae_conv_shapes_pair.jsonl) — what pays is a DOUBLE-BUFFERED accumulator
+      // (2 NT BN <= 512 columns) so that the epilogue of one super-tile overlaps the MMAs of the next: NT = 1 for the
+      // 192-wide tiles (1559 vs 1062 TF/s at NT = 2 on stage C), NT = 2 for the 96-wide ones (797 vs 660 / 702 at 1 / 4)
+      int nt = (BK == 64) ? 1 : 2;
       if (g_conv_nt < 0) {             // MV_CONV_NT=1|2|4 / mv_vae_conv_config: tiles per CTA (A/B measurements)
         const char* e = getenv("MV_CONV_NT");
         g_conv_nt = e ? atoi(e) : 0;

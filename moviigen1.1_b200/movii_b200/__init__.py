@@ -61,6 +61,7 @@ _SIGNATURES = {
     "mv_attention_fwd_trace": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr, _int, _ptr],
     "mv_attention_config": [_int, _int, _int, _int, _int],
     "mv_gemm_config": [_int],
+    "mv_roles_config": [_int],
     "mv_vae_conv_config": [_int, _int],
     "mv_t5_attention": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _int, _ptr],
     "mv_t5_rmsnorm": [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _f32, _ptr],
@@ -528,6 +529,11 @@ def attention_trace(q, k, v, out, trace, softmax_scale=None):
           Lq, k.shape[0], H, float(softmax_scale if softmax_scale is not None else 128 ** -0.5), _p(trace),
           trace.shape[1], _stream())
     return out
+
+
+def roles_config(hi=-1):
+    """Diagnostics: 1 = TMA / MMA role warps at the highest warp ids of every tcgen05 kernel, 0 = lowest."""
+    _check(lib().mv_roles_config(int(hi)), "mv_roles_config")
 
 
 def gemm_config(pair=-1):

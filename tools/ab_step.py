@@ -21,7 +21,8 @@ from wan.modules.model import WanModel  # noqa: E402
 def main():
     args = sys.argv[1:]
     workload = args[0] if args and args[0] in bench.WORKLOADS else "720p"
-    # variant = kstep:emu:stale:pingpong[:skew][,pair=0|1]   (pair: CTA-pair GEMM kernel for the large linears)
+    # variant = kstep:emu:stale:pingpong[:skew][,pair=0|1][,hi=0|1]   (pair: CTA-pair GEMM kernel; hi: role warps at the
+    # highest warp ids in every tcgen05 kernel)
     variants = [a for a in args if ":" in a] or ["128:0:1:0,pair=0", "128:0:1:0,pair=1", "128:0:1:0,pair=0"]
     dev = torch.device("cuda", 0)
     mv.device_check()
@@ -49,6 +50,8 @@ def main():
             k, _, v = o.partition("=")
             if k == "pair":
                 mv.gemm_config(int(v))
+            if k == "hi":
+                mv.roles_config(int(v))
         out = model([lat], t=t, context=ctx, seq_len=seq_len)[0]
         torch.cuda.synchronize()
         sampler = bench.ClockSampler(0)
