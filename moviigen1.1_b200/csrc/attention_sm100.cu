@@ -57,6 +57,7 @@ constexpr int kDefaultStale = 1;     // 128-key kernel: fixed-reference softmax 
                                      // 1137 vs 1067 TF/s inside the power-capped 720P step; MV_ATTN_STALE=0: classic online softmax
 constexpr int kDefaultKStep = 128;   // 128-key-step kernel below (in the 14B 720P step: 1019 vs 946 TF/s); MV_ATTN_KSTEP=64: the kernel above
 constexpr int kDefaultSkewNs = 0;
+constexpr int kDefaultWaitSpin = 0;   // 0: waiting warps are parked in hardware (mbar_wait); 1: they poll
 constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
 constexpr uint32_t kQHalfBytes = kQTileBytes / 2;    // [128 x 64] 128B-swizzled sub-tile
@@ -81,6 +82,8 @@ struct AttnParams {
                 // antiphase so that they do not queue on the MUFU pipe at the same time
   unsigned long long* trace;  // diagnostics (mv_attention_fwd_trace): clock64 stamps of CTA (0, 0), see the entry point
   int trace_steps;
+  int wait_spin;  // 1: the waits on the per-tile chain (scores ready, P ready, P.V done, K/V landed) poll instead of
+                  // parking the warp (MV_ATTN_WAIT_SPIN / mv_attention_config): A/B of the wake-up latency
   int order;  // 0 (default): Q_w K_{j+2}^T is issued after P_w V_j has drained (explicit o_done wait);
               // 1 (MV_ATTN_ORDER=1): issued right behind it, relying on in-order execution of the tensor pipe
 };
@@ -499,6 +502,11 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool spin = p.wait_spin != 0;
+  auto wait = [&](uint64_t* bar, uint32_t parity) {
+    if (spin) mbar_wait_spin(bar, parity);
+    else mbar_wait(bar, parity);
+  };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -516,7 +524,7 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       auto load_tile = [&](const CUtensorMap* tm, int j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        wait(&kv_empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&kv_full[stage], kKVTileBytes2);
           tma_load_3d(sKV + stage * kKVTileBytes2, tm, &kv_full[stage], 0, head, j * kBKV2);
@@ -569,8 +577,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           phase ^= 1;
         }
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[stage], phase);
+      wait(q_full, 0);
+      wait(&kv_full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
         issue_qk(stage);
@@ -587,9 +595,9 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const int kstage = stage;
         const uint32_t kphase = phase;
         if (more) advance();
-        mbar_wait(&kv_full[vstage], vphase);
-        if (more) mbar_wait(&kv_full[kstage], kphase);
-        mbar_wait(&p_full[w], j & 1);
+        wait(&kv_full[vstage], vphase);
+        if (more) wait(&kv_full[kstage], kphase);
+        wait(&p_full[w], j & 1);
         tc_fence_after();
         if constexpr (TRACE) {
           if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < p.trace_steps)
@@ -659,8 +667,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
         // P.V(j-1) completes before the scores of step j (same issuing thread, committed first): taking its phase
         // FIRST keeps the (free) probe off the path between "scores ready" and the first tcgen05.ld
-        if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);
-        mbar_wait(&s_full[wg], j & 1);
+        if (j > 0) wait(&o_done[wg], (j - 1) & 1);
+        wait(&s_full[wg], j & 1);
         if (j == 0 && wg == 1 && p.skew_ns > 0) {   // MV_ATTN_SKEW (clocks): one-time phase offset between the two tiles
           const long long t0 = clock64();
           while (clock64() - t0 < p.skew_ns) {}
@@ -749,8 +757,8 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       // phase is taken every step so that every phase of the barrier is observed in order.
       const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && quad == 0 && lane == 0 && j < p.trace_steps;
       unsigned long long* trow = TRACE ? p.trace + (wg * p.trace_steps + (tr ? j : 0)) * 8 : nullptr;
-      if (j > 0) mbar_wait(&o_done[wg], (j - 1) & 1);   // completes before s_full(j): probed first, off the S -> ld path
-      mbar_wait(&s_full[wg], j & 1);
+      if (j > 0) wait(&o_done[wg], (j - 1) & 1);   // completes before s_full(j): probed first, off the S -> ld path
+      wait(&s_full[wg], j & 1);
       tc_fence_after();
       if constexpr (TRACE) { if (tr) trow[0] = clock64(); }
       uint32_t s[4][32];
@@ -840,7 +848,7 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
 
     // ------------------------------ final epilogue ----------------------------
-    mbar_wait(&o_done[wg], (n_kv - 1) & 1);
+    wait(&o_done[wg], (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int row = q0 + wg * kBQ + quad * 32 + lane;
@@ -885,10 +893,10 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 // (A/B measurements inside one process; the product path never calls it).
 namespace {
 struct AttnKnobs {
-  int kstep, emu, stale, pingpong, order, skew;
+  int kstep, emu, stale, pingpong, order, skew, wait_spin;
   bool init;
 };
-AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, false};
+AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, 0, false};
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
@@ -904,13 +912,14 @@ AttnKnobs& attn_knobs() {
     g_knobs.pingpong = env_int("MV_ATTN_PINGPONG", mv::kDefaultPingPong);
     g_knobs.order = env_int("MV_ATTN_ORDER", 0) == 1 ? 1 : 0;   // default 0: same speed since each tile has its own issuer
     g_knobs.skew = env_int("MV_ATTN_SKEW", mv::kDefaultSkewNs);
+    g_knobs.wait_spin = env_int("MV_ATTN_WAIT_SPIN", mv::kDefaultWaitSpin) != 0 ? 1 : 0;
     g_knobs.init = true;
   }
   return g_knobs;
 }
 }  // namespace
 
-extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew) {
+extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew, int wait_spin) {
   AttnKnobs& kn = attn_knobs();
   if ((kstep >= 0 && kstep != 64 && kstep != 128) || emu > 2) {
     mv::set_error("mv_attention_config: kstep must be 64 or 128, emu 0..2 (negative = keep)");
@@ -921,6 +930,7 @@ extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, 
   if (stale >= 0) kn.stale = stale;
   if (pingpong >= 0) kn.pingpong = pingpong;
   if (skew >= 0) kn.skew = skew;
+  if (wait_spin >= 0) kn.wait_spin = wait_spin != 0 ? 1 : 0;
   return MV_OK;
 }
 
@@ -964,6 +974,7 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.order = kn.order;
   p.skew_ns = kn.skew;
+  p.wait_spin = kn.wait_spin;
   p.pingpong = kn.pingpong;
   p.trace = trace;
   p.trace_steps = trace_steps;

@@ -73,17 +73,48 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel (launch error reported through the
-// C ABI), never as a hung GPU.  The bound (MV_WAIT_TIMEOUT_NS) is far above any legitimate wait.
-#ifndef MV_WAIT_TIMEOUT_NS
-#define MV_WAIT_TIMEOUT_NS 4000000000ull
+// Blocking probe with a suspend-time hint: the hardware parks the warp until the phase completes or `ns` nanoseconds
+// have passed (the un-hinted form above returns after ~100 clk, which turns every waiting warp into a poller).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (launch error reported through the C ABI), never as
+// a hung GPU.  Waiting costs nothing: ncu showed the round-1 loop (un-hinted try_wait + a globaltimer read that the
+// compiler hoisted into every iteration) executing 2.4e8 times per 16 ms conv launch in the warps that wait for an
+// accumulator — 1/5 of the SM's issue slots and most of the XU pipe (profiles/README.md, round 2).  Now a waiting warp
+// sleeps in hardware (1 ms suspend hint, woken by the phase completion) and the bound is a count of those sleeps.
+#ifndef MV_WAIT_SLEEP_NS
+#define MV_WAIT_SLEEP_NS 1000000u
+#endif
+#ifndef MV_WAIT_MAX_SLEEPS
+#define MV_WAIT_MAX_SLEEPS 4000u   /* x 1 ms: far above any legitimate wait */
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint32_t sleeps = 0;
+  while (!mbar_try_wait_hint(bar, parity, MV_WAIT_SLEEP_NS)) {
+    if (++sleeps > MV_WAIT_MAX_SLEEPS) {
+      printf("mv: mbarrier wait timeout block(%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// Polling wait (un-hinted try_wait, ~100 clk per probe) for waits on a latency-critical chain, where the wake-up of a
+// parked warp would sit on the critical path; bounded by a probe count.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > MV_WAIT_TIMEOUT_NS) {
+    if (++spins > (1u << 26)) {
       printf("mv: mbarrier wait timeout block(%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
              threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -735,6 +735,57 @@ softmax_rows_kernel(const float* __restrict__ S, int64_t lds, __half* __restrict
   for (int i = threadIdx.x; i < N; i += blockDim.x) pr[i] = __float2half_rn(__expf((s[i] - mx) * scale) * inv);
 }
 
+// One pass: the whole row (N <= 1024 * 4 * kSmxVec floats) lives in the registers of a 1024-thread CTA — S is read
+// once (float4), P written once; the three-pass kernel above stays for longer rows.
+constexpr int kSmxVec = 8;   // float4 per thread -> N <= 32768
+__global__ void __launch_bounds__(1024)
+softmax_rows_reg_kernel(const float* __restrict__ S, int64_t lds, __half* __restrict__ P, int64_t ldp, int N, float scale) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float4* s4 = reinterpret_cast<const float4*>(S + row * lds);
+  const int nvec = N >> 2;
+  float4 v[kSmxVec];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmxVec; ++i) {
+    const int idx = threadIdx.x + i * 1024;
+    v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (idx < nvec) v[i] = s4[idx];
+    mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();
+  const float sl2 = scale * 1.4426950408889634f;
+  const float nm = -mx * sl2;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmxVec; ++i) {
+    v[i].x = fast_exp2(fmaf(v[i].x, sl2, nm));
+    v[i].y = fast_exp2(fmaf(v[i].y, sl2, nm));
+    v[i].z = fast_exp2(fmaf(v[i].z, sl2, nm));
+    v[i].w = fast_exp2(fmaf(v[i].w, sl2, nm));
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);      // exp2(-inf) = 0 for the padding lanes
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = warp_sum(red[lane]);
+  const float inv = 1.f / sum;
+  uint2* p2 = reinterpret_cast<uint2*>(P + row * ldp);
+#pragma unroll
+  for (int i = 0; i < kSmxVec; ++i) {
+    const int idx = threadIdx.x + i * 1024;
+    if (idx < nvec) p2[idx] = make_uint2(pack_f16(v[i].x * inv, v[i].y * inv), pack_f16(v[i].z * inv, v[i].w * inv));
+  }
+}
+
 template <int BK>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   static bool attr_set = false;
@@ -1045,6 +1096,13 @@ extern "C" int mv_softmax_rows(const float* S, int64_t lds, void* P_f16, int64_t
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(M > 0 && N > 0, "mv_softmax_rows: empty problem");
+  if ((N & 3) == 0 && (lds & 3) == 0 && (ldp & 3) == 0 && N <= 1024 * 4 * kSmxVec &&
+      (reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(P_f16) & 7) == 0) {
+    softmax_rows_reg_kernel<<<M, 1024, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, reinterpret_cast<__half*>(P_f16),
+                                                                              ldp, N, scale);
+    MV_CHECK_LAUNCH("softmax_rows_reg_kernel");
+    return MV_OK;
+  }
   softmax_rows_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, reinterpret_cast<__half*>(P_f16),
                                                                        ldp, N, scale);
   MV_CHECK_LAUNCH("softmax_rows_kernel");

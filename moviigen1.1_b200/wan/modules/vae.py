@@ -250,12 +250,19 @@ class VaeEngine:
     def _fusable(c):
         return c.cout <= 256 and c.cout == c.cout_real
 
-    def resblock(self, x, p, key):
+    def resblock(self, x, p, key, a_in=None, nxt=None):
+        """x -> x + conv(silu(norm(conv(silu(norm(x))))))  (vae.py:186-220).  a_in = (halo buffer, cached frames) when the
+        PRODUCER of x already wrote silu(rms_norm(x) * g0) into this block's first conv input; nxt = (gamma, cache key)
+        of the norm the CONSUMER applies to the result: when this block's last conv can hold a channel row per thread
+        it emits that normalised tensor too (returned as a_next), and the stand-alone pass over HBM disappears."""
         n, H, W, _ = x.shape
         h = x if p["sc"] is None else self.conv(x, p["sc"])
         c2, c6 = p["c2"], p["c6"]
-        a, ka = self.halo_buffer(key + ".c2", n, H, W, c2.cin)
-        self.normsilu(x, p["g0"], out=a[ka:])
+        if a_in is None:
+            a, ka = self.halo_buffer(key + ".c2", n, H, W, c2.cin)
+            self.normsilu(x, p["g0"], out=a[ka:])
+        else:
+            a, ka = a_in
         self.commit(key + ".c2", a)
         y, ky = self.halo_buffer(key + ".c6", n, H, W, c2.cout)
         if self._fusable(c2):
@@ -266,7 +273,14 @@ class VaeEngine:
             self.normsilu(y[ky:], p["g3"])
         del a
         self.commit(key + ".c6", y)
-        return self.conv(y, c6, res=h, t_off=ky)
+        if nxt is not None and self._fusable(c6):
+            gamma_n, key_n = nxt
+            an, kn = self.halo_buffer(key_n, n, H, W, c6.cout)
+            out = torch.empty(n, H, W, c6.cout, dtype=F16, device=self.device)
+            mv.vae_conv_fused(y, c6, out, gamma_n, an[kn:], res=h, o_base=0, os_t=H * W * c6.cout, os_h=W * c6.cout,
+                              os_w=c6.cout, t_off=ky)
+            return out, (an, kn)
+        return self.conv(y, c6, res=h, t_off=ky), None
 
     def attention(self, x, p):
         """vae.py:223-262: per-frame single-head attention, d = C, over the H*W positions."""
@@ -290,7 +304,7 @@ class VaeEngine:
             mv.gemm_f16(P, vT, None, Of[f * hw:(f + 1) * hw], mv.MV_EPI_BF16)
         return self.conv(O, p["proj"], res=x)
 
-    def upsample(self, x, p, key, first):
+    def upsample(self, x, p, key, first, nxt=None):
         T, H, W, C = x.shape
         if p["mode"] == "upsample3d":
             # time_conv (3,1,1) C -> 2C + frame interleave; its stream starts at frame 1 of the sequence and never
@@ -312,10 +326,17 @@ class VaeEngine:
             T = T2
         Co = C // 2
         out = torch.empty(T, 2 * H, 2 * W, Co, dtype=F16, device=self.device)
+        a_next = None
+        if nxt is not None and all(self._fusable(c) for c in p["par"].values()):
+            an, kn = self.halo_buffer(nxt[1], T, 2 * H, 2 * W, Co)
+            a_next = (an, kn)
         for (a, b), c in p["par"].items():
-            mv.vae_conv(x, c, out, res=None, o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co,
-                        os_w=2 * Co)
-        return out
+            kw = dict(o_base=(a * 2 * W + b) * Co, os_t=4 * H * W * Co, os_h=4 * W * Co, os_w=2 * Co)
+            if a_next is not None:
+                mv.vae_conv_fused(x, c, out, nxt[0], a_next[0][a_next[1]:], **kw)
+            else:
+                mv.vae_conv(x, c, out, res=None, **kw)
+        return out, a_next
 
     # -- WanVAE.decode for one latent ---------------------------------------------------------------------------
     def decode(self, z):
@@ -340,17 +361,27 @@ class VaeEngine:
                 mv.vae_latent_in(zc, self.w2, self.b2, self.mean, self.std, x[k:])
                 self.commit("conv1", x)
                 x = self.conv(x, self.conv1, t_off=k)
+                a_in = None          # silu(rms_norm(x)) already written into the next block's first conv input
+                nl = len(self.layers)
                 for i, (kind, p) in enumerate(self.layers):
-                    if kind == "res":
-                        x = self.resblock(x, p, "L%d" % i)
-                    elif kind == "attn":
-                        x = self.attention(x, p)
+                    if i + 1 < nl:
+                        nk, npar = self.layers[i + 1]
+                        nxt = (npar["g0"], "L%d.c2" % (i + 1)) if nk == "res" else None
                     else:
-                        x = self.upsample(x, p, "L%d" % i, first)
+                        nxt = (self.head_gamma, "head")
+                    if kind == "res":
+                        x, a_in = self.resblock(x, p, "L%d" % i, a_in=a_in, nxt=nxt)
+                    elif kind == "attn":
+                        x, a_in = self.attention(x, p), None
+                    else:
+                        x, a_in = self.upsample(x, p, "L%d" % i, first, nxt=nxt)
                 nt, H, W, C = x.shape
-                a, k = self.halo_buffer("head", nt, H, W, C)
-                self.normsilu(x, self.head_gamma, out=a[k:])
-                del x
+                if a_in is None:
+                    a, k = self.halo_buffer("head", nt, H, W, C)
+                    self.normsilu(x, self.head_gamma, out=a[k:])
+                else:
+                    a, k = a_in
+                del x, a_in
                 self.commit("head", a)
                 mv.vae_conv(a, self.head, video, res=None, out_mode=1, o_base=t_done * H * W, os_t=Tout * H * W, t_off=k)
                 del a

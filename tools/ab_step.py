@@ -52,6 +52,8 @@ def main():
                 mv.gemm_config(int(v))
             if k == "hi":
                 mv.roles_config(int(v))
+            if k == "spin":
+                mv.attention_config(wait_spin=int(v))
         out = model([lat], t=t, context=ctx, seq_len=seq_len)[0]
         torch.cuda.synchronize()
         sampler = bench.ClockSampler(0)

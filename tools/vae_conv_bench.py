@@ -61,7 +61,10 @@ def main():
             mv.vae_conv_config(-2, -2)
             print(json.dumps(rec), flush=True)
             continue
-        T, H, W, Ci, Co = STAGES[st]
+        if st.startswith("X:"):      # custom shape X:T:H:W:Cin:Cout (experiments on what bounds a channel plan)
+            T, H, W, Ci, Co = (int(v) for v in st.split(":")[1:])
+        else:
+            T, H, W, Ci, Co = STAGES[st]
         x = torch.randn(T + 2, H, W, Ci, device=DEV, generator=g).half()
         wt = torch.randn(Co, Ci, 3, 3, 3, device=DEV, generator=g) / math.sqrt(27 * Ci)
         c = _Conv(wt.cpu(), torch.zeros(Co), _taps(3, 3, 3), DEV)
