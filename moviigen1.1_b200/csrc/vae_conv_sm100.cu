@@ -417,6 +417,7 @@ struct Conv2Params {
   int dh_min, box_h;                        // A box: h from (tile origin + dh_min), box_h = 8 NT + dh_max - dh_min rows
   uint32_t a_box_bytes, b_slab_bytes, stage_bytes;   // 1024-aligned
   int stages, nbuf;
+  int regular3;                             // every group = the three vertical taps dh = dh_min, +1, +2 in order
   int sup_h, sup_w, num_super;              // super-tiles (pair = 16 NT x 16 voxels) per frame in h / w; total incl. t, n
 };
 
@@ -517,6 +518,45 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int buf = it % nbuf;
         const uint32_t use = static_cast<uint32_t>(it / nbuf);
         uint32_t started = 0;    // bit j: tile j has received its first MMA of this super-tile
+        if (q.regular3) {
+          // 3x3x3 / 3x3 tap sets: every (dt, dw) group holds the vertical taps dh = -1, 0, +1 in order, so all operand
+          // offsets inside a stage are compile-time constants and the issue sequence is straight-line code on uniform
+          // registers (3 x NT x BK/16 back-to-back UTCHMMAs per stage).  With 48-clock MMAs (N = 96) the general loop
+          // below (indexed constant loads + per-thread address math + R2UR per MMA) could not keep the tensor pipe fed.
+          const uint32_t dbase = tmem_base + static_cast<uint32_t>(buf * NT * p.BN);
+          const uint32_t bstep = q.b_slab_bytes >> 4;
+          for (int step = 0; step < steps_per_super; ++step) {
+            mbar_wait(&full[stage], phase);
+            if (step == 0) {
+              for (int j = 0; j < NT; ++j) mbar_wait(&tempty[buf * NT + j], (use & 1u) ^ 1u);   // accumulators drained
+            }
+            tc_fence_after();
+            const uint64_t a0 = desc0 + ((static_cast<uint32_t>(stage) * q.stage_bytes) >> 4);
+            const uint64_t b0 = a0 + (q.a_box_bytes >> 4);
+            const uint32_t acc0 = step > 0 ? 1u : 0u;
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < NT; ++j) {
+                const uint32_t d_tmem = dbase + static_cast<uint32_t>(j * p.BN);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_ss_pair(d_tmem, a0 + (((j * kConvTH + i) * kRowGroupBytes) >> 4) + 2 * k, b0 + i * bstep + 2 * k,
+                                 idesc, (i | k) != 0 ? 1u : acc0);
+                }
+              }
+              umma_commit_pair(&empty[stage], 3);
+              if (step == steps_per_super - 1) umma_commit_pair(&tfull[buf], 3);
+            }
+            __syncwarp();
+            if (++stage == nstages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int step = 0; step < steps_per_super; ++step) {
           const int g = step % q.ngroups;
           mbar_wait(&full[stage], phase);
@@ -900,8 +940,14 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
       ++q.g_ntap[g];
     }
     if (ok && dh_max - dh_min <= 2) {
-      for (int g = 0; g < q.ngroups; ++g)
-        for (int i = 0; i < q.g_ntap[g]; ++i) q.g_dhoff[g][i] = static_cast<int8_t>(q.g_dhoff[g][i] - dh_min);
+      q.regular3 = 1;
+      for (int g = 0; g < q.ngroups; ++g) {
+        for (int i = 0; i < q.g_ntap[g]; ++i) {
+          q.g_dhoff[g][i] = static_cast<int8_t>(q.g_dhoff[g][i] - dh_min);
+          if (q.g_dhoff[g][i] != i) q.regular3 = 0;
+        }
+        if (q.g_ntap[g] != 3) q.regular3 = 0;
+      }
       // tiles per CTA: measured (profiles/r02_vae_conv_shapes_pair.jsonl) — what pays is a DOUBLE-BUFFERED accumulator
       // (2 NT BN <= 512 columns) so that the epilogue of one super-tile overlaps the MMAs of the next: NT = 1 for the
       // 192-wide tiles (1559 vs 1062 TF/s at NT = 2 on stage C), NT = 2 for the 96-wide ones (797 vs 660 / 702 at 1 / 4)
