@@ -417,9 +417,33 @@ struct Conv2Params {
   int dh_min, box_h;                        // A box: h from (tile origin + dh_min), box_h = 8 NT + dh_max - dh_min rows
   uint32_t a_box_bytes, b_slab_bytes, stage_bytes;   // 1024-aligned
   int stages, nbuf;
-  int regular3;                             // every group = the three vertical taps dh = dh_min, +1, +2 in order
+  int regular;                              // n > 0: every group = n vertical taps dh = dh_min, dh_min + 1, ... in order
   int sup_h, sup_w, num_super;              // super-tiles (pair = 16 NT x 16 voxels) per frame in h / w; total incl. t, n
 };
+
+// One pipeline stage of the pair kernel for a regular tap group: NTAP vertical taps x NT tiles x BK/16 k-steps, issued by
+// the elected thread as straight-line code (every offset a compile-time constant), then the stage / accumulator commits.
+template <int BK, int NT, int NTAP>
+__device__ __forceinline__ void conv_issue_stage(uint64_t a0, uint64_t b0, uint32_t bstep, uint32_t dbase, int BN,
+                                                 uint32_t idesc, uint32_t acc0, uint64_t* empty_bar, uint64_t* tfull_bar) {
+  constexpr uint32_t kRowGroupBytes = kConvTW * ConvCfg<BK>::kRowBytes;   // one h row of the box = 16 voxels
+  if (elect_one()) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t d_tmem = dbase + static_cast<uint32_t>(j * BN);
+#pragma unroll
+      for (int i = 0; i < NTAP; ++i) {
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_ss_pair(d_tmem, a0 + (((j * kConvTH + i) * kRowGroupBytes) >> 4) + 2 * k, b0 + i * bstep + 2 * k, idesc,
+                       (i | k) != 0 ? 1u : acc0);
+      }
+    }
+    umma_commit_pair(empty_bar, 3);
+    if (tfull_bar != nullptr) umma_commit_pair(tfull_bar, 3);
+  }
+  __syncwarp();
+}
 
 template <int BK, int NT, bool HI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv2Threads, 1)
@@ -466,14 +490,16 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const int steps_per_super = p.kblocks_per_tap * q.ngroups;
 
-  // super-tile -> (n block fastest, then w, h, t)
+  // super-tile -> (n block fastest, then w, then t, then h): a band of rows is swept through ALL frames before the
+  // next band starts, so the two history frames a temporal tap re-reads are still in L2 (ncu on the (n, w, h, t)
+  // order: every input frame came from DRAM three times, 21 GB read for 10.4 GB of operands on the stage-D conv)
   auto decode = [&](int st, int& n_blk, int& t, int& h0, int& w0) {
     n_blk = st % p.num_n;
     int r = st / p.num_n;
     w0 = (r % q.sup_w) * kConvTW;
     r /= q.sup_w;
-    h0 = (r % q.sup_h) * (2 * NT * kConvTH) + static_cast<int>(rank) * (NT * kConvTH);   // this CTA's first row
-    t = r / q.sup_h;
+    t = r % p.T;
+    h0 = (r / p.T) * (2 * NT * kConvTH) + static_cast<int>(rank) * (NT * kConvTH);   // this CTA's first row
   };
 
   if (warp == 0) {
@@ -518,13 +544,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int buf = it % nbuf;
         const uint32_t use = static_cast<uint32_t>(it / nbuf);
         uint32_t started = 0;    // bit j: tile j has received its first MMA of this super-tile
-        if (q.regular3) {
-          // 3x3x3 / 3x3 tap sets: every (dt, dw) group holds the vertical taps dh = -1, 0, +1 in order, so all operand
-          // offsets inside a stage are compile-time constants and the issue sequence is straight-line code on uniform
-          // registers (3 x NT x BK/16 back-to-back UTCHMMAs per stage).  With 48-clock MMAs (N = 96) the general loop
-          // below (indexed constant loads + per-thread address math + R2UR per MMA) could not keep the tensor pipe fed.
+        if (q.regular > 0) {
+          // Regular tap sets (3x3x3: 3 vertical taps per (dt, dw) group; sub-pixel 2x2: 2; time_conv: 1 — always
+          // dh = dh_min, dh_min + 1, ... in order): all operand offsets inside a stage are compile-time constants and
+          // the issue sequence is straight-line code on uniform registers (NTAP x NT x BK/16 back-to-back UTCHMMAs per
+          // stage).  With 48-clock MMAs (N = 96) the general loop below (indexed constant loads + per-thread address
+          // math + R2UR per MMA) could not keep the tensor pipe fed: 36 % -> 70 % tensor-pipe active on stage D.
           const uint32_t dbase = tmem_base + static_cast<uint32_t>(buf * NT * p.BN);
-          const uint32_t bstep = q.b_slab_bytes >> 4;
           for (int step = 0; step < steps_per_super; ++step) {
             mbar_wait(&full[stage], phase);
             if (step == 0) {
@@ -534,22 +560,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t a0 = desc0 + ((static_cast<uint32_t>(stage) * q.stage_bytes) >> 4);
             const uint64_t b0 = a0 + (q.a_box_bytes >> 4);
             const uint32_t acc0 = step > 0 ? 1u : 0u;
-            if (elect_one()) {
-#pragma unroll
-              for (int j = 0; j < NT; ++j) {
-                const uint32_t d_tmem = dbase + static_cast<uint32_t>(j * p.BN);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                  for (int k = 0; k < BK / 16; ++k)
-                    umma_ss_pair(d_tmem, a0 + (((j * kConvTH + i) * kRowGroupBytes) >> 4) + 2 * k, b0 + i * bstep + 2 * k,
-                                 idesc, (i | k) != 0 ? 1u : acc0);
-                }
-              }
-              umma_commit_pair(&empty[stage], 3);
-              if (step == steps_per_super - 1) umma_commit_pair(&tfull[buf], 3);
-            }
-            __syncwarp();
+            const bool last = step == steps_per_super - 1;
+            if (q.regular == 3) conv_issue_stage<BK, NT, 3>(a0, b0, q.b_slab_bytes >> 4, dbase, p.BN, idesc, acc0, &empty[stage], last ? &tfull[buf] : nullptr);
+            else if (q.regular == 2) conv_issue_stage<BK, NT, 2>(a0, b0, q.b_slab_bytes >> 4, dbase, p.BN, idesc, acc0, &empty[stage], last ? &tfull[buf] : nullptr);
+            else conv_issue_stage<BK, NT, 1>(a0, b0, q.b_slab_bytes >> 4, dbase, p.BN, idesc, acc0, &empty[stage], last ? &tfull[buf] : nullptr);
             if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
@@ -940,13 +954,13 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
       ++q.g_ntap[g];
     }
     if (ok && dh_max - dh_min <= 2) {
-      q.regular3 = 1;
+      q.regular = q.g_ntap[0];
       for (int g = 0; g < q.ngroups; ++g) {
         for (int i = 0; i < q.g_ntap[g]; ++i) {
           q.g_dhoff[g][i] = static_cast<int8_t>(q.g_dhoff[g][i] - dh_min);
-          if (q.g_dhoff[g][i] != i) q.regular3 = 0;
+          if (q.g_dhoff[g][i] != i) q.regular = 0;
         }
-        if (q.g_ntap[g] != 3) q.regular3 = 0;
+        if (q.g_ntap[g] != q.g_ntap[0]) q.regular = 0;
       }
       // tiles per CTA: measured (profiles/r02_vae_conv_shapes_pair.jsonl) — what pays is a DOUBLE-BUFFERED accumulator
       // (2 NT BN <= 512 columns) so that the epilogue of one super-tile overlaps the MMAs of the next: NT = 1 for the
