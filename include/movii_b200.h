@@ -253,8 +253,9 @@ int mv_roles_config(int hi);
  * _PINGPONG / _SKEW) for A/B timing inside one process; a negative argument keeps the current value.  kstep 64 | 128,
  * emu 0..2 (fraction of exponentials on the FMA pipe: none, 1/4, 1/2), stale 1 = fixed-reference softmax (128-key
  * kernel), skew = one-time start offset of the second Q tile (clocks), wait_spin 1 = the waits on the per-tile chain
- * poll instead of parking the warp.  tools/ab_step.py. */
-int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew, int wait_spin);
+ * poll instead of parking the warp, pack 1 = P packed to bf16 by a truncating PRMT of pre-scaled exponentials instead of
+ * F2FP conversions.  tools/ab_step.py. */
+int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew, int wait_spin, int pack);
 
 /* ---- umT5 text encoder (caller side of the hot path) --------------------------- */
 

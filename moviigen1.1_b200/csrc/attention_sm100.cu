@@ -57,7 +57,10 @@ constexpr int kDefaultStale = 1;     // 128-key kernel: fixed-reference softmax 
                                      // 1137 vs 1067 TF/s inside the power-capped 720P step; MV_ATTN_STALE=0: classic online softmax
 constexpr int kDefaultKStep = 128;   // 128-key-step kernel below (in the 14B 720P step: 1019 vs 946 TF/s); MV_ATTN_KSTEP=64: the kernel above
 constexpr int kDefaultSkewNs = 0;
-constexpr int kDefaultWaitSpin = 0;   // 0: waiting warps are parked in hardware (mbar_wait); 1: they poll
+constexpr int kDefaultWaitSpin = 0;
+constexpr int kDefaultPrmtPack = 0;   // 1: truncating PRMT pack of P (PK) — MV_ATTN_PACK / mv_attention_config
+constexpr float kPkScale = 1.0f + 3.0f / 1024.0f;
+constexpr float kPkLog2 = 0.0042205915f;   // log2(1 + 3/1024)   // 0: waiting warps are parked in hardware (mbar_wait); 1: they poll
 constexpr int kDefaultPingPong = 0;   // skewing the two warpgroups' start had no measurable effect
 constexpr uint32_t kQTileBytes = kBQ * kD * 2;       // 32 KB
 constexpr uint32_t kQHalfBytes = kQTileBytes / 2;    // [128 x 64] 128B-swizzled sub-tile
@@ -455,7 +458,7 @@ constexpr uint32_t kKVTileBytes2 = kBKV2 * kD * 2;     // 32 KB
 constexpr uint32_t kKVHalfBytes2 = kKVTileBytes2 / 2;  // [128 x 64] sub-tile
 constexpr uint32_t kAttnSmem2 = 2 * kQTileBytes + kKVStages2 * kKVTileBytes2 + 1024 + 512;
 
-template <int EMU, bool PP, bool TRACE, bool STALE, bool HI = false>
+template <int EMU, bool PP, bool TRACE, bool STALE, bool HI = false, bool PK = false>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -710,7 +713,11 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll 1
         do {
           const float2 sc2 = make_float2(sl2, sl2);
-          const float2 nm2 = make_float2(-ref2, -ref2);
+          // PK: P is rounded to bf16 by TRUNCATING 2^(x + log2(1 + 3/1024)) — the pre-scale adds 0.375..0.75 bf16 ulp, i.e.
+          // round-to-nearest up to a sub-ulp threshold shift with ~zero mean bias — so the pack is one PRMT on the ALU pipe
+          // instead of one F2FP conversion per pair on the pipe the exponentials run on; the constant is folded into the
+          // FFMA that exists anyway and divided out of the row sum at the end (kPkScale).
+          const float2 nm2 = make_float2(-ref2 + (PK ? kPkLog2 : 0.f), -ref2 + (PK ? kPkLog2 : 0.f));
           sum2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -727,8 +734,13 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 e23.x = fast_exp2(x23.x);
                 e23.y = (EMU >= 1) ? exp2_emu(fminf(x23.y, 126.f)) : fast_exp2(x23.y);
                 sum2 = __fadd2_rn(sum2, __fadd2_rn(e01, e23));
-                pk[h][cc * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
-                pk[h][cc * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
+                if constexpr (PK) {
+                  pk[h][cc * 16 + (i >> 1)] = __byte_perm(__float_as_uint(e01.x), __float_as_uint(e01.y), 0x7632);
+                  pk[h][cc * 16 + (i >> 1) + 1] = __byte_perm(__float_as_uint(e23.x), __float_as_uint(e23.y), 0x7632);
+                } else {
+                  pk[h][cc * 16 + (i >> 1)] = pack_bf16(e01.x, e01.y);
+                  pk[h][cc * 16 + (i >> 1) + 1] = pack_bf16(e23.x, e23.y);
+                }
               }
             }
           }
@@ -850,7 +862,7 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     // ------------------------------ final epilogue ----------------------------
     wait(&o_done[wg], (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
+    const float inv_l = (PK && STALE ? kPkScale : 1.0f) / l_run;   // the row sum carries the pre-scale of the truncating pack
     const int row = q0 + wg * kBQ + quad * 32 + lane;
     __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * kD;
     if (p.n_dst > 0 && row < p.Lq) {
@@ -893,10 +905,10 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 // (A/B measurements inside one process; the product path never calls it).
 namespace {
 struct AttnKnobs {
-  int kstep, emu, stale, pingpong, order, skew, wait_spin;
+  int kstep, emu, stale, pingpong, order, skew, wait_spin, pack;
   bool init;
 };
-AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, 0, false};
+AttnKnobs g_knobs = {0, 0, 0, 0, 0, 0, 0, 0, false};
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
@@ -913,13 +925,14 @@ AttnKnobs& attn_knobs() {
     g_knobs.order = env_int("MV_ATTN_ORDER", 0) == 1 ? 1 : 0;   // default 0: same speed since each tile has its own issuer
     g_knobs.skew = env_int("MV_ATTN_SKEW", mv::kDefaultSkewNs);
     g_knobs.wait_spin = env_int("MV_ATTN_WAIT_SPIN", mv::kDefaultWaitSpin) != 0 ? 1 : 0;
+    g_knobs.pack = env_int("MV_ATTN_PACK", mv::kDefaultPrmtPack) != 0 ? 1 : 0;
     g_knobs.init = true;
   }
   return g_knobs;
 }
 }  // namespace
 
-extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew, int wait_spin) {
+extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, int skew, int wait_spin, int pack) {
   AttnKnobs& kn = attn_knobs();
   if ((kstep >= 0 && kstep != 64 && kstep != 128) || emu > 2) {
     mv::set_error("mv_attention_config: kstep must be 64 or 128, emu 0..2 (negative = keep)");
@@ -931,6 +944,7 @@ extern "C" int mv_attention_config(int kstep, int emu, int stale, int pingpong, 
   if (pingpong >= 0) kn.pingpong = pingpong;
   if (skew >= 0) kn.skew = skew;
   if (wait_spin >= 0) kn.wait_spin = wait_spin != 0 ? 1 : 0;
+  if (pack >= 0) kn.pack = pack != 0 ? 1 : 0;
   return MV_OK;
 }
 
@@ -1023,6 +1037,8 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                                        static_cast<int>(kAttnSmem2)));
     MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kAttnSmem2)));
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_k128_kernel<0, false, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kAttnSmem2)));
   }
   dim3 grid((Lq + 2 * kBQ - 1) / (2 * kBQ), H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1031,6 +1047,7 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     if (stale && !p.pingpong && emu <= 1 && softmax_scale > 0.f) {
       if (p.trace != nullptr) attention_fwd_k128_kernel<0, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else if (emu == 1) attention_fwd_k128_kernel<1, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
+      else if (kn.pack) attention_fwd_k128_kernel<0, false, false, true, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else if (roles_hi()) attention_fwd_k128_kernel<0, false, false, true, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
       else attention_fwd_k128_kernel<0, false, false, true><<<grid, kAttnThreads, kAttnSmem2, st>>>(tmQ, tmK, tmV, p);
     } else

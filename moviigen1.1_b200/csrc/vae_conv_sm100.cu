@@ -402,7 +402,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   1, 3 ...), each thread one voxel row of its tile (conv_epilogue_tile above).
 // ================================================================================================================
 constexpr int kConv2Threads = 320;
-constexpr int kDefaultConvPair = 0;   // flipped to 1 once validated and measured on the GPU (profiles/)
+constexpr int kDefaultConvPair = 1;   // measured: 1080P decode 47 -> 73 fps (profiles/r02_vae_*); MV_CONV_PAIR=0 = single-CTA kernel
 constexpr int kConv2MaxGroups = 9;
 constexpr int kConv2MaxStages = 6;
 constexpr uint32_t kConv2RingBytes = 216 * 1024;

@@ -59,7 +59,7 @@ _SIGNATURES = {
     "mv_linear_f32_vec": [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _ptr],
     "mv_sinusoid_embed": [_ptr, _int, _ptr, _int, _ptr],
     "mv_attention_fwd_trace": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _f32, _ptr, _int, _ptr],
-    "mv_attention_config": [_int, _int, _int, _int, _int, _int],
+    "mv_attention_config": [_int, _int, _int, _int, _int, _int, _int],
     "mv_gemm_config": [_int],
     "mv_roles_config": [_int],
     "mv_vae_conv_config": [_int, _int],
@@ -547,7 +547,8 @@ def vae_conv_config(pair=-1, tiles_per_cta=-1):
     _check(lib().mv_vae_conv_config(int(pair), int(tiles_per_cta)), "mv_vae_conv_config")
 
 
-def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, skew=-1, wait_spin=-1):
+def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, skew=-1, wait_spin=-1, pack=-1):
     """Diagnostics: pick the attention kernel variant for subsequent launches (negative = keep); tools/ab_step.py."""
-    _check(lib().mv_attention_config(int(kstep), int(emu), int(stale), int(pingpong), int(skew), int(wait_spin)),
+    _check(lib().mv_attention_config(int(kstep), int(emu), int(stale), int(pingpong), int(skew), int(wait_spin),
+                                       int(pack)),
            "mv_attention_config")

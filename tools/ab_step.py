@@ -54,6 +54,8 @@ def main():
                 mv.roles_config(int(v))
             if k == "spin":
                 mv.attention_config(wait_spin=int(v))
+            if k == "pack":
+                mv.attention_config(pack=int(v))
         out = model([lat], t=t, context=ctx, seq_len=seq_len)[0]
         torch.cuda.synchronize()
         sampler = bench.ClockSampler(0)
