@@ -229,6 +229,26 @@ int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_
 int mv_vae_latent_in(const float* z, const float* W2, const float* b2, const float* mean, const float* stdv,
                      void* out_cl, int Z, int64_t nvox, mv_stream_t stream);
 
+/* ---- WanVAE encoder (vae.py:265-366,516-542) --------------------------------------------------------
+ * Strided convolution on the same implicit GEMM: out[t,h,w,:] = bias + sum_taps in[st*t + t_off + dt, sh*h + dh,
+ * sw*w + dw, :] . W_tap^T, strides 1 or 2; the A operand is a TMA box with traversal strides, taps running past the far
+ * edge read zeros.  Serves Resample 'downsample2d/3d': ZeroPad2d((0,1,0,1)) + Conv2d(3x3, stride 2) (taps dh, dw in
+ * 0..2; vae.py:92-104) and the time_conv (3,1,1) stride (2,1,1) on [last cached frame | chunk] (t_off = 2, taps
+ * dt = -2..0; vae.py:143-159).  in_T = st*(out_T-1) + t_off + 1.  fp16 channels-last in and out. */
+int mv_vae_conv_strided(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed, const float* bias,
+                        void* out_cl, int out_T, int out_H, int out_W, int Cout, int ntaps, const int8_t* taps_dt_dh_dw,
+                        int t_off, int stride_t, int stride_h, int stride_w, mv_stream_t stream);
+
+/* Frames [t0, t0+n) of a channel-first fp32 video [3, T_total, H, W] -> fp16 channels-last [n, H, W, 16] (channels
+ * 3..15 zero), the stem conv's operand (vae.py:286,519-530). */
+int mv_vae_video_in(const float* video, int T_total, int t0, int n, int H, int W, void* out_cl, mv_stream_t stream);
+
+/* mu[o, mu_off + v] = ((sum_c W1[o,c] * head[v,c] + b1[o]) - mean[o]) * inv_std[o] for o < Z: conv1 (1x1x1, 2Z -> 2Z,
+ * mu half only), `.chunk(2)` and the latent normalisation (vae.py:531-537); head fp16 channels-last [nvox, 2Z], mu fp32
+ * channel-first with mu_plane elements per channel. */
+int mv_vae_latent_out(const void* head_cl, const float* W1, const float* b1, const float* mean, const float* inv_std,
+                      float* mu, int Z, int64_t nvox, int64_t mu_plane, int64_t mu_off, mv_stream_t stream);
+
 /* P_f16[m, :N] = softmax(S[m, :N] * scale) (fp32 in, fp16 out): the softmax of the VAE's single-head attention between the
  * two tcgen05 GEMMs (vae.py:246-257). */
 int mv_softmax_rows(const float* S, int64_t lds, void* P_f16, int64_t ldp, int M, int N, float scale,

@@ -87,6 +87,12 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 int make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  return make_tmap_bf16_es(map, base, rank, dims, strides_bytes, box, swizzle_bytes, nullptr);
+}
+
+int make_tmap_bf16_es(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
+                      const uint32_t* elem_strides) {
   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
   if (swizzle_bytes == 128) swz = CU_TENSOR_MAP_SWIZZLE_128B;
   else if (swizzle_bytes == 64) swz = CU_TENSOR_MAP_SWIZZLE_64B;
@@ -115,7 +121,11 @@ int make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = (elem_strides != nullptr && i > 0) ? elem_strides[i] : 1;   // traversal stride: box[i] / es[i] elements land
+    if (es[i] < 1 || es[i] > 8 || box[i] % es[i] != 0) {
+      set_error("TMA traversal stride %u (dim %d, box %u) unsupported", es[i], i, box[i]);
+      return MV_E_SHAPE;
+    }
     if (i > 0) {
       gstr[i - 1] = strides_bytes[i];
       if (strides_bytes[i] % 16 != 0) {

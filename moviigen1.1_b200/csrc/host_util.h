@@ -29,6 +29,11 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 // Same with an explicit swizzle span: 128, 64, 32 (bytes; must equal box[0] * 2) or 0 (none).
 int make_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+// + traversal strides per dimension (elem_strides[0] ignored): dimension i delivers box[i] / elem_strides[i] elements,
+// every elem_strides[i]-th one — the A operand of a strided convolution without a gather pass
+int make_tmap_bf16_es(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
+                      const uint32_t* elem_strides);
 
 #define MV_CHECK_CUDA(expr)                                \
   do {                                                     \

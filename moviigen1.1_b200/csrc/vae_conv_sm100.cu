@@ -44,6 +44,8 @@ struct ConvParams {
   int T, H, W;                  // output grid (stride-1 "same" convolutions: input H, W equal; input T = t_off + T)
   int t_off;                    // output frame t reads input frames t + t_off + dt: the first t_off input frames are the
                                 // cached tail of the previous temporal chunk (CausalConv3d feature cache, vae.py:28-36,205-217)
+  int st, sh, sw;               // convolution strides (encoder downsampling, vae.py:92-104): output voxel (t,h,w) reads input
+                                // (st*t + t_off + dt, sh*h + dh, sw*w + dw); the TMA map carries sh / sw as traversal strides
   int Cin, Cout;
   int BN;                       // N tile (multiple of 16, <= 256)
   int ntaps;
@@ -309,7 +311,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int tap = (kb + i) / p.kblocks_per_tap;
             const int cb = (kb + i) - tap * p.kblocks_per_tap;
             tma_load_4d(sA + stage * kConvABytesMax + i * p.a_block_bytes, &tmA, &full[stage], cb * BK,
-                        w0 + p.dw[tap], h0 + p.dh[tap], t + p.t_off + p.dt[tap]);
+                        p.sw * w0 + p.dw[tap], p.sh * h0 + p.dh[tap], p.st * t + p.t_off + p.dt[tap]);
             tma_load_2d(sB + stage * kConvBBytesMax + i * p.b_block_bytes, &tmB, &full[stage],
                         tap * p.Cin + cb * BK, n_blk * p.BN);
           }
@@ -758,6 +760,56 @@ __global__ void vae_latent_in_kernel(const float* __restrict__ z, const float* _
 }
 
 // --------------------------------------------------------------------------------------------
+// Encoder edges.  video_in: frames [t0, t0+n) of a channel-first fp32 video [3, T, H, W] -> channels-last fp16
+// [n, H, W, 16] (channels 3..15 zero: the 16-channel K block of the stem conv, vae.py:286).
+// latent_out: conv1 (1x1x1, 2Z -> 2Z; only the mu half is computed) on the fp16 head output [nvox, 2Z], then
+// mu = (mu - mean) * (1 / std), written channel-first fp32                                   vae.py:531-537
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vae_video_in_kernel(const float* __restrict__ video, int64_t chan_stride, int64_t base, int64_t nvox,
+                    uint4* __restrict__ out) {
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float r = video[base + v], g = video[chan_stride + base + v], b = video[2 * chan_stride + base + v];
+    uint4 lo;
+    lo.x = pack_f16(f16_sat(r), f16_sat(g));
+    lo.y = pack_f16(f16_sat(b), 0.f);
+    lo.z = 0u;
+    lo.w = 0u;
+    out[2 * v] = lo;
+    out[2 * v + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vae_latent_out_kernel(const __half* __restrict__ head, const float* __restrict__ W1, const float* __restrict__ b1,
+                      const float* __restrict__ mean, const float* __restrict__ inv_std, float* __restrict__ mu, int Z,
+                      int64_t nvox, int64_t mu_plane, int64_t mu_off) {
+  __shared__ float sw[16 * 32 + 48];
+  const int C = 2 * Z;
+  float* sb = sw + Z * C;
+  float* sm = sb + Z;
+  float* ss = sm + Z;
+  for (int i = threadIdx.x; i < Z * C; i += blockDim.x) sw[i] = W1[i];      // rows 0..Z-1 of the [2Z, 2Z] matrix = mu
+  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
+    sb[i] = b1[i];
+    sm[i] = mean[i];
+    ss[i] = inv_std[i];
+  }
+  __syncthreads();
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float x[32];
+    for (int c = 0; c < C; ++c) x[c] = __half2float(head[v * C + c]);
+    for (int o = 0; o < Z; ++o) {
+      float acc = sb[o];
+      for (int c = 0; c < C; ++c) acc = fmaf(sw[o * C + c], x[c], acc);
+      mu[o * mu_plane + mu_off + v] = __fmul_rn(__fsub_rn(acc, sm[o]), ss[o]);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // Row softmax for the VAE's single-head attention: P = softmax(S * scale), S fp32 [M, N] -> P fp16 [M, ldp].
 // One CTA per row.                                                                 vae.py:246-257
 // --------------------------------------------------------------------------------------------
@@ -903,16 +955,32 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
                          const float* bias, const void* res_cl, void* out, int out_mode, int out_T, int out_H,
                          int out_W, int Cout, int cout_real, int ntaps, const int8_t* taps_dt_dh_dw, int64_t o_base,
                          int64_t os_t, int64_t os_h, int64_t os_w, int nsplit, int64_t nsplit_off,
-                         const float* norm_gamma, void* norm_out, int t_off, mv_stream_t stream) {
+                         const float* norm_gamma, void* norm_out, int t_off, mv_stream_t stream, int stride_t = 1,
+                         int stride_h = 1, int stride_w = 1) {
   int rc = require_sm100();
   if (rc != MV_OK) return rc;
   MV_REQUIRE(ntaps >= 1 && ntaps <= kConvMaxTaps, "mv_vae_conv: ntaps=%d out of range", ntaps);
   MV_REQUIRE(Cin % 16 == 0 && Cin >= 16, "mv_vae_conv: Cin=%d must be a multiple of 16", Cin);
   MV_REQUIRE(Cout % 16 == 0, "mv_vae_conv: (padded) Cout=%d must be a multiple of 16", Cout);
   MV_REQUIRE(out_T > 0 && out_H > 0 && out_W > 0, "mv_vae_conv: empty output grid");
-  MV_REQUIRE(t_off >= 0 && in_T == out_T + t_off && in_H == out_H && in_W == out_W,
-             "mv_vae_conv: input grid %dx%dx%d does not match output %dx%dx%d + %d cached frames", in_T, in_H, in_W, out_T,
-             out_H, out_W, t_off);
+  const bool strided = stride_t != 1 || stride_h != 1 || stride_w != 1;
+  if (!strided) {
+    MV_REQUIRE(t_off >= 0 && in_T == out_T + t_off && in_H == out_H && in_W == out_W,
+               "mv_vae_conv: input grid %dx%dx%d does not match output %dx%dx%d + %d cached frames", in_T, in_H, in_W,
+               out_T, out_H, out_W, t_off);
+  } else {
+    // strided: the last output voxel's first tap must lie inside the input; taps that run past the far edge read the
+    // TMA zero fill (= ZeroPad2d((0,1,0,1)), vae.py:93-94)
+    MV_REQUIRE(stride_t >= 1 && stride_t <= 2 && stride_h >= 1 && stride_h <= 2 && stride_w >= 1 && stride_w <= 2,
+               "mv_vae_conv_strided: strides %d,%d,%d out of range (1 or 2)", stride_t, stride_h, stride_w);
+    MV_REQUIRE(t_off >= 0 && in_T == stride_t * (out_T - 1) + t_off + 1,
+               "mv_vae_conv_strided: %d input frames != %d * (%d - 1) + %d + 1", in_T, stride_t, out_T, t_off);
+    MV_REQUIRE(stride_h * (out_H - 1) < in_H && stride_w * (out_W - 1) < in_W && stride_h * out_H + 1 >= in_H &&
+                   stride_w * out_W + 1 >= in_W,
+               "mv_vae_conv_strided: output %dx%d does not cover input %dx%d at stride %d,%d", out_H, out_W, in_H, in_W,
+               stride_h, stride_w);
+    MV_REQUIRE(norm_out == nullptr && out_mode == 0, "mv_vae_conv_strided: plain fp16 output only");
+  }
   int BK = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
   int BN;
   if (Cout <= 256) BN = Cout;
@@ -930,7 +998,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   MV_REQUIRE(out != nullptr || norm_out != nullptr, "mv_vae_conv: no output");
 
   // ---- CTA-pair kernel (conv_igemm_pair_kernel) for the tensor-bound convolutions -----------------------------------
-  if (conv_pair_enabled() && (BK == 64 || BK == 32) && BN % 16 == 0 && ntaps >= 2) {
+  if (conv_pair_enabled() && !strided && (BK == 64 || BK == 32) && BN % 16 == 0 && ntaps >= 2) {
     Conv2Params q;
     memset(&q, 0, sizeof(q));
     bool ok = true;
@@ -1000,6 +1068,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
         p.nsplit_off = nsplit_off;
         p.T = out_T;
         p.t_off = t_off;
+        p.st = p.sh = p.sw = 1;
         p.H = out_H;
         p.W = out_W;
         p.Cin = Cin;
@@ -1039,9 +1108,10 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
     uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)Cin * in_W * 2, (uint64_t)Cin * in_W * in_H * 2};
-    uint32_t box[4] = {(uint32_t)BK, kConvTW, kConvTH, 1};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)(kConvTW * stride_w), (uint32_t)(kConvTH * stride_h), 1};
+    uint32_t es[4] = {1, (uint32_t)stride_w, (uint32_t)stride_h, 1};
     // (a 16-bit tensor map only moves bytes: the bf16 encoder serves fp16 data unchanged)
-    rc = make_tmap_bf16_sw(&tmA, in_cl, 4, dims, str, box, BK * 2);
+    rc = make_tmap_bf16_es(&tmA, in_cl, 4, dims, str, box, BK * 2, es);
     if (rc != MV_OK) return rc;
   }
   {
@@ -1063,6 +1133,9 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   p.nsplit_off = nsplit_off;
   p.T = out_T;
   p.t_off = t_off;
+  p.st = stride_t;
+  p.sh = stride_h;
+  p.sw = stride_w;
   p.H = out_H;
   p.W = out_W;
   p.Cin = Cin;
@@ -1115,6 +1188,46 @@ extern "C" int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W
                                  mv_stream_t stream) {
   return vae_conv_impl(in_cl, in_T, in_H, in_W, Cin, w_packed, bias, res_cl, out, 0, out_T, out_H, out_W, Cout, Cout,
                        ntaps, taps_dt_dh_dw, o_base, os_t, os_h, os_w, 0, 0, norm_gamma, norm_out, t_off, stream);
+}
+
+extern "C" int mv_vae_conv_strided(const void* in_cl, int in_T, int in_H, int in_W, int Cin, const void* w_packed,
+                                   const float* bias, void* out_cl, int out_T, int out_H, int out_W, int Cout, int ntaps,
+                                   const int8_t* taps_dt_dh_dw, int t_off, int stride_t, int stride_h, int stride_w,
+                                   mv_stream_t stream) {
+  return vae_conv_impl(in_cl, in_T, in_H, in_W, Cin, w_packed, bias, nullptr, out_cl, 0, out_T, out_H, out_W, Cout, Cout,
+                       ntaps, taps_dt_dh_dw, 0, static_cast<int64_t>(out_H) * out_W * Cout,
+                       static_cast<int64_t>(out_W) * Cout, Cout, 0, 0, nullptr, nullptr, t_off, stream, stride_t, stride_h,
+                       stride_w);
+}
+
+extern "C" int mv_vae_video_in(const float* video, int T_total, int t0, int n, int H, int W, void* out_cl,
+                               mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(n > 0 && t0 >= 0 && t0 + n <= T_total && H > 0 && W > 0, "mv_vae_video_in: bad frame range / shape");
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  const int64_t nvox = plane * n;
+  int64_t blocks = (nvox + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  vae_video_in_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      video, static_cast<int64_t>(T_total) * plane, static_cast<int64_t>(t0) * plane, nvox,
+      reinterpret_cast<uint4*>(out_cl));
+  MV_CHECK_LAUNCH("vae_video_in_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_vae_latent_out(const void* head_cl, const float* W1, const float* b1, const float* mean,
+                                 const float* inv_std, float* mu, int Z, int64_t nvox, int64_t mu_plane, int64_t mu_off,
+                                 mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(Z > 0 && Z <= 16 && nvox > 0 && mu_off >= 0 && mu_off + nvox <= mu_plane, "mv_vae_latent_out: bad shape");
+  int64_t blocks = (nvox + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  vae_latent_out_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(head_cl), W1, b1, mean, inv_std, mu, Z, nvox, mu_plane, mu_off);
+  MV_CHECK_LAUNCH("vae_latent_out_kernel");
+  return MV_OK;
 }
 
 extern "C" int mv_vae_rmsnorm_silu(const void* x_cl, void* y_cl, const float* gamma, int64_t nvox, int C, int silu,

@@ -46,6 +46,10 @@ _SIGNATURES = {
     "mv_vae_rmsnorm_silu": [_ptr, _ptr, _ptr, _i64, _int, _int, _ptr],
     "mv_vae_latent_in": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _ptr],
     "mv_softmax_rows": [_ptr, _i64, _ptr, _i64, _int, _int, _f32, _ptr],
+    "mv_vae_conv_strided": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _ptr, _int,
+                            _int, _int, _int, _ptr],
+    "mv_vae_video_in": [_ptr, _int, _int, _int, _int, _int, _ptr, _ptr],
+    "mv_vae_latent_out": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _i64, _i64, _ptr],
     "mv_ipc_export": [_ptr, _ptr, _ptr, _ptr],
     "mv_ipc_open": [_ptr, _ptr],
     "mv_ipc_close": [_ptr],
@@ -392,6 +396,46 @@ def vae_latent_in(z, w2, b2, mean, std, out):
     assert out.is_contiguous() and out.numel() == z.numel() and out.shape[-1] == Z
     _call("mv_vae_latent_in", _p(z), _p(w2), _p(b2), _p(mean), _p(std), _p(out), Z, nvox, _stream())
     return out
+
+
+def vae_conv_strided(x, conv, out, stride=(1, 2, 2), t_off=0):
+    """Strided conv (encoder downsampling): x [Tin,H,W,Cin] fp16 channels-last -> out [T,Ho,Wo,Cout] fp16 channels-last,
+    out voxel (t,h,w) reads x[st*t + t_off + dt, sh*h + dh, sw*w + dw]; reads past the far edge are zeros."""
+    _req(x, torch.float16, "x"); _req(conv.w, torch.float16, "w"); _req(conv.b, torch.float32, "bias")
+    _req(out, torch.float16, "out")
+    assert x.dim() == 4 and out.dim() == 4 and x.is_contiguous() and out.is_contiguous() and conv.w.is_contiguous()
+    Tin, H, W, Cin = x.shape
+    T, Ho, Wo, Co = out.shape
+    assert Cin == conv.cin and Co == conv.cout and conv.taps.device.type == "cpu" and conv.taps.dtype == torch.int8
+    st, sh, sw = (int(v) for v in stride)
+    _call("mv_vae_conv_strided", _p(x), Tin, H, W, Cin, _p(conv.w), _p(conv.b), _p(out), T, Ho, Wo, Co, conv.ntaps,
+          conv.taps.data_ptr(), int(t_off), st, sh, sw, _stream())
+    return out
+
+
+def vae_video_in(video, t0, n, out):
+    """video [3,T,H,W] fp32 (contiguous) frames [t0, t0+n) -> out [n,H,W,16] fp16 channels-last (channels 3.. zero)."""
+    _req(video, torch.float32, "video"); _req(out, torch.float16, "out")
+    assert video.dim() == 4 and video.shape[0] == 3 and video.is_contiguous() and out.is_contiguous()
+    _, T, H, W = video.shape
+    assert tuple(out.shape) == (n, H, W, 16)
+    _call("mv_vae_video_in", _p(video), T, int(t0), int(n), H, W, _p(out), _stream())
+    return out
+
+
+def vae_latent_out(head, w1, b1, mean, inv_std, mu, t0):
+    """head [n,h,w,2Z] fp16 -> mu[:, t0:t0+n] of the fp32 channel-first latent [Z,T,h,w] (conv1 + chunk + normalise)."""
+    _req(head, torch.float16, "head"); _req(mu, torch.float32, "mu")
+    for t, nme in ((w1, "w1"), (b1, "b1"), (mean, "mean"), (inv_std, "inv_std")):
+        _req(t, torch.float32, nme)
+        assert t.is_contiguous()
+    assert head.is_contiguous() and mu.is_contiguous() and head.dim() == 4 and mu.dim() == 4
+    n, h, w, C = head.shape
+    Z, T = mu.shape[0], mu.shape[1]
+    assert C == 2 * Z and tuple(mu.shape[2:]) == (h, w) and t0 + n <= T and tuple(w1.shape) == (C, C)
+    _call("mv_vae_latent_out", _p(head), _p(w1), _p(b1), _p(mean), _p(inv_std), _p(mu), Z, n * h * w, T * h * w,
+          int(t0) * h * w, _stream())
+    return mu
 
 
 def softmax_rows(s, p, n, scale):

@@ -1,10 +1,11 @@
-"""WanVAE with the reference's wrapper surface (wan/modules/vae.py:619-663) and decoder parameter names, decoded
-by the B200-native implicit-GEMM kernels (csrc/vae_conv_sm100.cu) through the C ABI.
+"""WanVAE with the reference's wrapper surface (wan/modules/vae.py:619-663) and parameter names, run by the
+B200-native implicit-GEMM kernels (csrc/vae_conv_sm100.cu) through the C ABI.
 
-Scope: the DECODER (WanVAE.decode) — the encoder is preprocessing only and out of scope.
-The decode is one pass over the whole latent sequence (the reference's 21 single-frame chunks + feature cache are
-a causal network; the only irregularity — upsample3d's time_conv starting at frame 1, the 'Rep' branch — is
-reproduced exactly; SURVEY.md Appendix B, pinned by tests/golden/vae_*.pt).
+WanVAE.decode (the hot path) and WanVAE.encode (§8f-4: preprocessing / i2v side, same kernels plus
+strided convolutions).  Both walk the sequence in temporal chunks with a feature cache like the reference; the
+networks are causal, so any chunking gives the same bits.  The irregularities are reproduced exactly: upsample3d's
+time_conv starts at frame 1 (the 'Rep' branch), downsample3d passes frame 0 through and strides over
+[last cached frame | chunk] (pinned by tests/golden/vae_decode.pt / vae_encode.pt).
 Activations and conv operands are channels-last FP16 [T, H, W, C] (the 10 mantissa bits the reference's TF32 convs keep;
 max-abs 4e-3 against the fp32 reference, bf16 storage measured 3e-2); accumulation is fp32.
 """
@@ -62,6 +63,34 @@ class _Up(nn.Module):
             self.time_conv = nn.Conv3d(dim, dim * 2, (3, 1, 1))
 
 
+class _Down(nn.Module):
+    def __init__(self, dim, mode):
+        super().__init__()
+        self.mode = mode
+        self.resample = nn.Sequential(nn.Identity(), nn.Conv2d(dim, dim, 3, stride=2))     # [0] = ZeroPad2d((0,1,0,1))
+        if mode == "downsample3d":
+            self.time_conv = nn.Conv3d(dim, dim, (3, 1, 1), stride=(2, 1, 1))
+
+
+class _Encoder(nn.Module):
+    """Parameter holder for Encoder3d (vae.py:265-321)."""
+
+    def __init__(self, dim, z_dim, dim_mult, num_res_blocks, temperal_downsample):
+        super().__init__()
+        dims = [dim * u for u in [1] + list(dim_mult)]
+        self.conv1 = nn.Conv3d(3, dims[0], 3)
+        downs = []
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(num_res_blocks):
+                downs.append(_Res(cin, cout))
+                cin = cout
+            if i != len(dim_mult) - 1:
+                downs.append(_Down(cout, "downsample3d" if temperal_downsample[i] else "downsample2d"))
+        self.downsamples = nn.Sequential(*downs)
+        self.middle = nn.Sequential(_Res(cout, cout), _Attn(cout), _Res(cout, cout))
+        self.head = nn.Sequential(_Gamma(cout, False), nn.Identity(), nn.Conv3d(cout, z_dim, 3))
+
+
 class _Decoder(nn.Module):
     def __init__(self, dim, z_dim, dim_mult, num_res_blocks, temperal_upsample):
         super().__init__()
@@ -82,7 +111,7 @@ class _Decoder(nn.Module):
 
 
 class WanVAE_(nn.Module):
-    """Decoder half of the reference's WanVAE_ (vae.py:481-514): `conv2` + `decoder`, same parameter names."""
+    """The reference's WanVAE_ (vae.py:481-514): `encoder` + `conv1`, `conv2` + `decoder`, same parameter names."""
 
     def __init__(self, dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
                  temperal_downsample=(False, True, True), dropout=0.0):
@@ -91,6 +120,8 @@ class WanVAE_(nn.Module):
             raise NotImplementedError("attn_scales must be empty (the shipped VAE config, vae.py:597-604)")
         self.dim, self.z_dim = dim, z_dim
         self.temperal_upsample = tuple(temperal_downsample)[::-1]
+        self.encoder = _Encoder(dim, z_dim * 2, tuple(dim_mult), num_res_blocks, tuple(temperal_downsample))
+        self.conv1 = nn.Conv3d(z_dim * 2, z_dim * 2, 1)
         self.conv2 = nn.Conv3d(z_dim, z_dim, 1)
         self.decoder = _Decoder(dim, z_dim, tuple(dim_mult), num_res_blocks, self.temperal_upsample)
         self._engine = None
@@ -106,8 +137,11 @@ class WanVAE_(nn.Module):
         return r
 
     def load_state_dict(self, sd, strict=True, **k):
-        """Reference checkpoints also carry the encoder (`encoder.*`, `conv1.*`): out of scope, dropped here."""
-        sd = {n: v for n, v in sd.items() if n.startswith("decoder.") or n.startswith("conv2.")}
+        """A state dict holding only one half (decoder + conv2, or encoder + conv1) leaves the other half untouched."""
+        mine = self.state_dict()
+        for half in (("decoder.", "conv2."), ("encoder.", "conv1.")):
+            if not any(n.startswith(half) for n in sd):
+                sd = {**{n: v for n, v in mine.items() if n.startswith(half)}, **sd}
         r = super().load_state_dict(sd, strict=strict, **k)
         self._engine = None
         return r
@@ -116,6 +150,10 @@ class WanVAE_(nn.Module):
         """z [1, z_dim, T, h, w] -> [1, 3, 1+4(T-1), 8h, 8w] (vae.py:544-568); scale is accepted for API parity and
         must be the standard (mean, 1/std) pair."""
         return self.engine().decode(z[0]).unsqueeze(0)
+
+    def encode(self, x, scale=None):
+        """x [1, 3, 1+4k, H, W] in [-1, 1] -> normalised mu [1, z_dim, 1+k, H/8, W/8] (vae.py:516-542)."""
+        return self.engine().encode(x[0]).unsqueeze(0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,6 +240,8 @@ class VaeEngine:
         # 16 frames instead of 81).
         self.chunk = max(1, int(os.environ.get("MOVII_VAE_CHUNK", "4")))
         self.cache = {}
+        self.model = model
+        self.enc = None              # encoder plan, packed on the first encode()
 
     def _res(self, m):
         dev = self.device
@@ -392,6 +432,115 @@ class VaeEngine:
         return video
 
 
+    # -- WanVAE.encode ---------------------------------------------------------------------------
+    def _pack_encoder(self):
+        m, dev = self.model, self.device
+        e = m.encoder
+        f32 = lambda t: t.detach().to(F32).contiguous().to(dev)  # noqa: E731
+        w1 = e.conv1.weight.detach()
+        w1 = torch.cat([w1, w1.new_zeros(w1.shape[0], 16 - w1.shape[1], *w1.shape[2:])], dim=1)   # Cin 3 -> 16 (zeros)
+        layers = []
+        for mod in list(e.downsamples) + list(e.middle):
+            if isinstance(mod, _Res):
+                layers.append(("res", self._res(mod)))
+            elif isinstance(mod, _Attn):
+                layers.append(("attn", dict(
+                    gamma=f32(mod.norm.gamma.reshape(-1)),
+                    qkv=_Conv(mod.to_qkv.weight.unsqueeze(2), mod.to_qkv.bias, _taps(1, 1, 1), dev),
+                    proj=_Conv(mod.proj.weight.unsqueeze(2), mod.proj.bias, _taps(1, 1, 1), dev))))
+            else:
+                # ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2): taps at (2h + kh, 2w + kw), zeros past the far edge
+                down = dict(mode=mod.mode, sp=_Conv(mod.resample[1].weight.unsqueeze(2), mod.resample[1].bias,
+                                                    [(0, kh, kw) for kh in range(3) for kw in range(3)], dev))
+                if mod.mode == "downsample3d":
+                    down["time"] = _Conv(mod.time_conv.weight, mod.time_conv.bias, _taps(3, 1, 1), dev)
+                layers.append(("down", down))
+        zz = 2 * self.z_dim
+        self.enc = dict(conv1=_Conv(w1, e.conv1.bias, _taps(3, 3, 3), dev), layers=layers,
+                        head_gamma=f32(e.head[0].gamma.reshape(-1)),
+                        head=_Conv(e.head[2].weight, e.head[2].bias, _taps(3, 3, 3), dev),
+                        w1=f32(m.conv1.weight.reshape(zz, zz)), b1=f32(m.conv1.bias),
+                        inv_std=(1.0 / self.std).contiguous())
+        # input frames per pass after the first frame (a multiple of 4: the two stride-2 time convs stay aligned)
+        self.enc_chunk = max(4, int(os.environ.get("MOVII_VAE_ENC_CHUNK", "8")) // 4 * 4)
+
+    def downsample(self, x, p, key, first):
+        """Resample 'downsample2d' / 'downsample3d' (vae.py:92-104,140-159)."""
+        T, H, W, C = x.shape
+        Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+        if p["mode"] == "downsample2d":
+            return mv.vae_conv_strided(x, p["sp"], torch.empty(T, Ho, Wo, C, dtype=F16, device=self.device), (1, 2, 2))
+        # time_conv (3,1,1) stride (2,1,1), no temporal padding, over [last frame of the previous chunk | chunk]; the
+        # first chunk (frame 0 alone) only fills the cache and passes through (:146-148)
+        if first:
+            assert T == 1
+            y = mv.vae_conv_strided(x, p["sp"], torch.empty(1, Ho, Wo, C, dtype=F16, device=self.device), (1, 2, 2))
+            self.cache[key + ".t"] = y.clone()
+            return y
+        assert T % 2 == 0
+        xin = torch.empty(1 + T, Ho, Wo, C, dtype=F16, device=self.device)
+        xin[:1].copy_(self.cache[key + ".t"])
+        mv.vae_conv_strided(x, p["sp"], xin[1:], (1, 2, 2))
+        self.cache[key + ".t"] = xin[-1:].clone()
+        return mv.vae_conv_strided(xin, p["time"], torch.empty(T // 2, Ho, Wo, C, dtype=F16, device=self.device),
+                                   (2, 1, 1), t_off=2)
+
+    def encode(self, video):
+        """video [3, 1+4k, H, W] fp32 in [-1, 1] -> normalised mu [z_dim, 1+k, H/8, W/8] fp32 (vae.py:516-542, 650-655)."""
+        if self.enc is None:
+            self._pack_encoder()
+        E = self.enc
+        _, T, H, W = video.shape
+        if H % 8 or W % 8:
+            raise ValueError("WanVAE.encode: H and W must be multiples of 8, got %dx%d" % (H, W))
+        T = 1 + (T - 1) // 4 * 4                         # the reference drops frames that do not fill a chunk (:521-530)
+        video = video.to(self.device, F32).contiguous()
+        Tl = 1 + (T - 1) // 4
+        mu = torch.empty(self.z_dim, Tl, H // 8, W // 8, dtype=F32, device=self.device)
+        self.cache = {}
+        t_done = 0
+        try:
+            c0 = 0
+            while c0 < T:
+                first = c0 == 0
+                n = 1 if first else min(self.enc_chunk, T - c0)
+                x, k = self.halo_buffer("E.conv1", n, H, W, 16)
+                mv.vae_video_in(video, c0, n, x[k:])
+                self.commit("E.conv1", x)
+                x = self.conv(x, E["conv1"], t_off=k)
+                a_in = None
+                layers = E["layers"]
+                for i, (kind, p) in enumerate(layers):
+                    nxt = None
+                    if i + 1 < len(layers):
+                        if layers[i + 1][0] == "res":
+                            nxt = (layers[i + 1][1]["g0"], "E%d.c2" % (i + 1))
+                    else:
+                        nxt = (E["head_gamma"], "E.head")
+                    if kind == "res":
+                        x, a_in = self.resblock(x, p, "E%d" % i, a_in=a_in, nxt=nxt)
+                    elif kind == "attn":
+                        x, a_in = self.attention(x, p), None
+                    else:
+                        x, a_in = self.downsample(x, p, "E%d" % i, first), None
+                nt, h, w, C = x.shape
+                if a_in is None:
+                    a, k = self.halo_buffer("E.head", nt, h, w, C)
+                    self.normsilu(x, E["head_gamma"], out=a[k:])
+                else:
+                    a, k = a_in
+                del x, a_in
+                self.commit("E.head", a)
+                hd = self.conv(a, E["head"], t_off=k)
+                mv.vae_latent_out(hd, E["w1"], E["b1"], self.mean, E["inv_std"], mu, t_done)
+                t_done += nt
+                c0 += n
+        finally:
+            self.cache = {}
+        assert t_done == Tl
+        return mu
+
+
 class WanVAE:
     """wan/modules/vae.py:619-663.  vae_pth=None (or a missing file) -> random-init weights (benchmarks)."""
 
@@ -407,10 +556,13 @@ class WanVAE:
             self.model.load_state_dict(torch.load(vae_pth, map_location="cpu", weights_only=True))
         else:
             nn.init.normal_(self.model.decoder.middle[1].proj.weight, std=0.02)  # zero-init would hide the attention
+            nn.init.normal_(self.model.encoder.middle[1].proj.weight, std=0.02)
         self.model.eval().requires_grad_(False).to(device)
 
     def encode(self, videos):
-        raise NotImplementedError("the VAE encoder is preprocessing-only and outside the B200 hot path")
+        """videos: list of [3, 1+4k, H, W] in [-1, 1] -> list of normalised latents mu [16, 1+k, H/8, W/8] fp32 (:650-655)."""
+        eng = self.model.engine()
+        return [eng.encode(u) for u in videos]
 
     def decode(self, zs):
         """zs: list of [16, T, h, w] latents -> list of [3, 1+4(T-1), 8h, 8w] fp32 in [-1, 1]."""

@@ -142,6 +142,26 @@ def golden_vae(vae):
     return res
 
 
+def golden_vae_encode(vae):
+    """Reference chunked encode (WanVAE_.encode: 1 + 4 + 4 ... frames with its feature cache) on small videos: T = 1 (no
+    time_conv at all), 5 (one cached frame), 9 / 13 (steady state); H x W multiples of 8 incl. ragged 8x16 tiles."""
+    from oracle.vae_oracle import VAE_MEAN, VAE_STD
+    m = vae.WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                    temperal_downsample=[False, True, True]).eval()
+    fill_parameters([(n, p) for n, p in m.named_parameters() if n.startswith(("encoder.", "conv1."))], 505)
+    mean, std = torch.tensor(VAE_MEAN), torch.tensor(VAE_STD)
+    res = {"seed": 505, "cases": {}}
+    res["param_shapes"] = {k: tuple(v.shape) for k, v in m.state_dict().items()
+                           if k.startswith("encoder.") or k.startswith("conv1.")}
+    for T, H, W in ((1, 16, 24), (5, 24, 40), (9, 16, 16), (13, 32, 16)):
+        g = torch.Generator().manual_seed(200 + T)
+        x = (torch.rand(3, T, H, W, generator=g) * 2 - 1).to(torch.float16).float()     # fp16-exact pixels in [-1, 1]
+        with torch.no_grad():
+            mu = m.encode(x[None], [mean, 1.0 / std]).float()[0]
+        res["cases"][(T, H, W)] = dict(x=x.to(torch.float16), mu=mu)
+    return res
+
+
 def golden_dpmpp():
     """Trajectory of the reference FlowDPMSolverMultistepScheduler driven like text2video.py:214-223 (needs the
     diffusers stubs installed by golden_unipc)."""
@@ -200,14 +220,14 @@ def golden_t5():
 
 
 def main():
+    """python oracle/make_golden.py [name ...]: mint all goldens, or only the named ones (e.g. vae_encode)."""
     os.makedirs(OUT, exist_ok=True)
     att, model, vae = ref_loader.load_reference()
-    torch.save(golden_vae(vae), os.path.join(OUT, "vae_decode.pt"))
-    torch.save(golden_block_cfg1(model), os.path.join(OUT, "block_cfg1.pt"))
-    torch.save(golden_model_tiny(model), os.path.join(OUT, "model_tiny_hd128.pt"))
-    torch.save(golden_unipc(), os.path.join(OUT, "unipc.pt"))
-    torch.save(golden_dpmpp(), os.path.join(OUT, "dpmpp.pt"))
-    torch.save(golden_t5(), os.path.join(OUT, "t5_encoder.pt"))
+    jobs = {"vae_decode": lambda: golden_vae(vae), "vae_encode": lambda: golden_vae_encode(vae),
+            "block_cfg1": lambda: golden_block_cfg1(model), "model_tiny_hd128": lambda: golden_model_tiny(model),
+            "unipc": golden_unipc, "dpmpp": golden_dpmpp, "t5_encoder": golden_t5}
+    for name in (sys.argv[1:] or list(jobs)):
+        torch.save(jobs[name](), os.path.join(OUT, name + ".pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,4 +1,4 @@
-"""CPU oracle for the WanVAE decoder — TEST INFRASTRUCTURE ONLY (see oracle/dit_oracle.py for the rules).
+"""CPU oracle for the WanVAE decoder and encoder — TEST INFRASTRUCTURE ONLY (see oracle/dit_oracle.py for the rules).
 
 Restates WanVAE.decode (/root/reference/wan/modules/vae.py:657-663 -> WanVAE_.decode :544-568 -> Decoder3d.forward
 :423-472) functionally over the reference-named state dict, as ONE pass over the whole latent sequence: the
@@ -6,6 +6,11 @@ reference's 21 single-frame chunks with a 2-frame feature cache are mathematical
 CausalConv3d sees two zero frames in front), except that each `upsample3d` applies its time_conv to frames 1..T-1
 only and passes frame 0 through (the 'Rep' branch, :106-131) — SURVEY.md Appendix B.  Pinned against outputs of the
 reference's own chunked decode for T = 1, 2, 3, 5 (tests/golden/vae_*.pt, oracle/make_golden.py).
+
+`encode` restates WanVAE.encode (:650-655 -> WanVAE_.encode :516-542 -> Encoder3d.forward :323-366) the same way: the
+reference's 1 + 4 + 4 + ... frame chunks with the feature cache are a causal network, except that each `downsample3d`
+passes frame 0 through and computes y_k = time_conv(x_{2k-2}, x_{2k-1}, x_{2k}) for k >= 1 (:143-159).  Pinned against
+the reference's own chunked encode for T = 1, 5, 9, 13 (tests/golden/vae_encode.pt).
 
 `rb` emulates the storage contract of the CUDA path (rb = f16_rt: fp16 activations between layers, fp16 conv operands,
 fp32 accumulation; bf16_rt: the round-1 contract, kept for comparison); rb = ident gives the reference's fp32 semantics.
@@ -127,3 +132,54 @@ def decode(sd, z, rb=ident, dim=96, z_dim=16):
     x = rb(F.silu(rms_norm(x, sd["decoder.head.0.gamma"])))
     x = causal_conv3d(x, sd["decoder.head.2.weight"], sd["decoder.head.2.bias"], rb)
     return x[0].float().clamp_(-1, 1)
+
+
+def resample_down(sd, pre, x, mode, rb=ident):
+    """vae.py:66-160 for 'downsample2d' / 'downsample3d' in whole-sequence form: ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2)
+    per frame; 'downsample3d' then applies time_conv (3,1,1) stride (2,1,1) WITHOUT temporal padding to
+    [last frame of the previous chunk | chunk]; the first chunk (frame 0) skips it (:146-148)."""
+    b, c, t, h, w = x.shape
+    xf = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    xf = F.conv2d(F.pad(rb(xf), (0, 1, 0, 1)), rb(sd[pre + "resample.1.weight"].float()),
+                  sd[pre + "resample.1.bias"].float(), stride=2)
+    x = rb(xf.reshape(b, t, c, xf.shape[2], xf.shape[3]).permute(0, 2, 1, 3, 4))
+    if mode == "downsample3d" and t > 1:
+        tail = F.conv3d(rb(x), rb(sd[pre + "time_conv.weight"].float()), sd[pre + "time_conv.bias"].float(),
+                        stride=(2, 1, 1))                          # frames (0,1,2), (2,3,4), ... = y_1, y_2, ...
+        x = torch.cat([x[:, :, :1], rb(tail)], dim=2)
+    return x
+
+
+def encoder_plan(dim=96, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True)):
+    """Module list of Encoder3d.downsamples (vae.py:288-305): [('res', in, out) | ('down3d'|'down2d', dim)]."""
+    dims = [dim * u for u in [1] + list(dim_mult)]
+    plan = []
+    for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(num_res_blocks):
+            plan.append(("res", in_dim, out_dim))
+            in_dim = out_dim
+        if i != len(dim_mult) - 1:
+            plan.append(("down3d" if temperal_downsample[i] else "down2d", out_dim))
+    return dims, plan
+
+
+def encode(sd, video, rb=ident, dim=96, z_dim=16):
+    """WanVAE.encode for one video [3, 1+4k, H, W] fp32 in [-1, 1] -> mu [z_dim, 1+k, H/8, W/8] fp32, normalised."""
+    assert (video.shape[1] - 1) % 4 == 0, "the reference drops trailing frames that do not fill a 4-frame chunk (:521)"
+    x = rb(causal_conv3d(video.float().unsqueeze(0), sd["encoder.conv1.weight"], sd["encoder.conv1.bias"], rb))
+    _, plan = encoder_plan(dim)
+    for i, item in enumerate(plan):
+        pre = "encoder.downsamples.%d." % i
+        if item[0] == "res":
+            x = residual_block(sd, pre, x, rb)
+        else:
+            x = resample_down(sd, pre, x, "downsample3d" if item[0] == "down3d" else "downsample2d", rb)
+    x = residual_block(sd, "encoder.middle.0.", x, rb)
+    x = attention_block(sd, "encoder.middle.1.", x, rb)
+    x = residual_block(sd, "encoder.middle.2.", x, rb)
+    x = rb(F.silu(rms_norm(x, sd["encoder.head.0.gamma"])))
+    x = rb(causal_conv3d(x, sd["encoder.head.2.weight"], sd["encoder.head.2.bias"], rb))
+    mu = F.conv3d(x, sd["conv1.weight"].float(), sd["conv1.bias"].float())[:, :z_dim]   # :531 (fp32 in the kernel too)
+    mean = torch.tensor(VAE_MEAN[:z_dim]).view(1, z_dim, 1, 1, 1)
+    inv_std = (1.0 / torch.tensor(VAE_STD[:z_dim])).view(1, z_dim, 1, 1, 1)
+    return ((mu - mean) * inv_std)[0]                                                   # :532-537

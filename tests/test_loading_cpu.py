@@ -1,6 +1,6 @@
 """CPU: diffusers-free checkpoint loading: WanModel.from_pretrained reads config.json + *.safetensors
 exactly as the reference's ModelMixin.from_pretrained call (wan/text2video.py:87) expects them; WanVAE_ accepts a full
-reference VAE state dict (encoder keys dropped)."""
+reference VAE state dict (both halves)."""
 import json
 import os
 
@@ -35,8 +35,12 @@ def test_vae_accepts_full_reference_state_dict():
     from wan.modules.vae import WanVAE_
     m = WanVAE_()
     sd = {k: v.clone() for k, v in m.state_dict().items()}
-    sd["encoder.conv1.weight"] = torch.zeros(96, 3, 3, 3, 3)   # encoder / conv1 keys of Wan2.1_VAE.pth are ignored
+    sd["encoder.conv1.weight"] = torch.full((96, 3, 3, 3, 3), 0.5)   # Wan2.1_VAE.pth carries both halves
     sd["conv1.weight"] = torch.zeros(32, 32, 1, 1, 1)
     sd["decoder.head.2.bias"] = torch.full((3,), 0.25)
     m.load_state_dict(sd)
     assert torch.equal(m.decoder.head[2].bias.detach(), torch.full((3,), 0.25))
+    assert torch.equal(m.encoder.conv1.weight.detach(), torch.full((96, 3, 3, 3, 3), 0.5))
+    # a decoder-only state dict (what round-1 checkpoints of this repo hold) leaves the encoder half as it is
+    m.load_state_dict({k: v for k, v in sd.items() if k.startswith(("decoder.", "conv2."))})
+    assert torch.equal(m.encoder.conv1.weight.detach(), torch.full((96, 3, 3, 3, 3), 0.5))

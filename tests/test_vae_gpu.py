@@ -28,7 +28,16 @@ def vae():
     from wan.modules.vae import WanVAE_
     g = torch.load(os.path.join(GOLD, "vae_decode.pt"), weights_only=False)
     m = WanVAE_().eval().requires_grad_(False)
-    fill_parameters(m, g["seed"])
+    fill_parameters([(n, q) for n, q in m.named_parameters() if n.startswith(("decoder.", "conv2."))], g["seed"])
+    return m.to(DEV), g
+
+
+@pytest.fixture(scope="module")
+def vae_enc():
+    from wan.modules.vae import WanVAE_
+    g = torch.load(os.path.join(GOLD, "vae_encode.pt"), weights_only=False)
+    m = WanVAE_().eval().requires_grad_(False)
+    fill_parameters([(n, q) for n, q in m.named_parameters() if n.startswith(("encoder.", "conv1."))], g["seed"])
     return m.to(DEV), g
 
 
@@ -158,3 +167,111 @@ def test_vae_conv_pair_matches_single_cta(shape, mode, nt):
     assert torch.isfinite(b).all()
     assert (a - b).abs().max().item() <= 4e-3 * max(1.0, a.abs().max().item()), (a - b).abs().max().item()
     assert ((a - b).norm() / a.norm()).item() <= 5e-4
+
+
+# ---- encoder ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(1, 16, 24), (5, 24, 40), (9, 16, 16), (13, 32, 16)])
+def test_vae_encode_matches_reference_golden(vae_enc, case, conv_kernel):
+    """WanVAE.encode against the REFERENCE's chunked encode (1 + 4 + 4 ... frames, feature cache).  The fp16 storage
+    contract measures max-abs 8e-4..1.2e-3 on latents of magnitude ~1.5 in the CPU emulation (oracle f16_rt); asserted
+    with margin: max-abs <= 5e-3, rel-L2 <= 2e-3."""
+    m, g = vae_enc
+    rec = g["cases"][case]
+    x = rec["x"].float()
+    mu = m.encode(x[None].to(DEV))[0].cpu()
+    ref = rec["mu"]
+    T, H, W = case
+    assert mu.shape == ref.shape == (16, 1 + (T - 1) // 4, H // 8, W // 8) and mu.dtype == torch.float32
+    assert torch.isfinite(mu).all()
+    sd = state_dict_like(g["param_shapes"], g["seed"])
+    emu = V.encode(sd, x, V.f16_rt)
+    err, err_emu = (mu - ref).abs().max().item(), (emu - ref).abs().max().item()
+    assert err <= 5e-3, (err, err_emu)
+    assert ((mu - ref).norm() / ref.norm()).item() <= 2e-3
+    assert (mu - emu).abs().max().item() <= 5e-3
+
+
+def test_vae_encode_chunking_is_exact(vae_enc):
+    """Any 4-aligned chunking of the frames after the first gives the same bits (causal network + feature cache)."""
+    m, g = vae_enc
+    x = g["cases"][(13, 32, 16)]["x"].float().to(DEV)
+    eng = m.engine()
+    eng.encode(x)                        # packs the encoder, sets enc_chunk
+    keep = eng.enc_chunk
+    try:
+        eng.enc_chunk = 64
+        whole = eng.encode(x).clone()
+        for c in (4, 8):
+            eng.enc_chunk = c
+            assert torch.equal(eng.encode(x), whole), c
+    finally:
+        eng.enc_chunk = keep
+
+
+def test_vae_encode_drops_incomplete_chunk(vae_enc):
+    """T = 7 encodes frames 0..4 only, like the reference's `iter_ = 1 + (t - 1) // 4` (vae.py:521)."""
+    m, g = vae_enc
+    x = g["cases"][(9, 16, 16)]["x"].float().to(DEV)
+    assert torch.equal(m.encode(x[None, :, :7])[0], m.encode(x[None, :, :5])[0])
+    with pytest.raises(ValueError):
+        m.encode(x[None, :, :5, :12])
+
+
+@pytest.mark.parametrize("shape", [(2, 22, 36, 96, 96), (1, 16, 64, 192, 192), (3, 10, 6, 384, 384)])
+def test_vae_conv_strided_spatial(shape):
+    """ZeroPad2d((0,1,0,1)) + Conv2d(3x3, stride 2) through TMA traversal strides vs torch, ragged output tiles."""
+    import torch.nn.functional as F
+    import movii_b200 as mv
+    from wan.modules.vae import _Conv
+    T, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(T, H, W, Ci, generator=g).half()
+    wt = torch.randn(Co, Ci, 3, 3, generator=g) / math.sqrt(9 * Ci)
+    b = torch.randn(Co, generator=g)
+    c = _Conv(wt.unsqueeze(2), b, [(0, kh, kw) for kh in range(3) for kw in range(3)], DEV)
+    out = torch.full((T, H // 2, W // 2, Co), float("nan"), dtype=torch.float16, device=DEV)
+    mv.vae_conv_strided(x.to(DEV), c, out, (1, 2, 2))
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), V.f16_rt(wt), b, stride=2).permute(0, 2, 3, 1)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 4e-3, err
+
+
+def test_vae_conv_strided_temporal():
+    """time_conv (3,1,1) stride (2,1,1) over [cached frame | 4 frames] -> 2 frames (vae.py:100-101,156-157)."""
+    import torch.nn.functional as F
+    import movii_b200 as mv
+    from wan.modules.vae import _Conv, _taps
+    g = torch.Generator().manual_seed(4)
+    n, H, W, C = 8, 9, 20, 192
+    x = torch.randn(1 + n, H, W, C, generator=g).half()
+    wt = torch.randn(C, C, 3, 1, 1, generator=g) / math.sqrt(3 * C)
+    b = torch.randn(C, generator=g)
+    c = _Conv(wt, b, _taps(3, 1, 1), DEV)
+    out = torch.full((n // 2, H, W, C), float("nan"), dtype=torch.float16, device=DEV)
+    mv.vae_conv_strided(x.to(DEV), c, out, (2, 1, 1), t_off=2)
+    ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], V.f16_rt(wt), b, stride=(2, 1, 1))[0].permute(1, 2, 3, 0)
+    assert (out.float().cpu() - ref).abs().max().item() <= 4e-3
+    with pytest.raises(RuntimeError):
+        mv.vae_conv_strided(x[:-1].to(DEV), c, out, (2, 1, 1), t_off=2)       # frame count does not match the stride
+
+
+def test_vae_encoder_edges():
+    """video_in (channel-first fp32 -> channels-last fp16, 3 -> 16 channels) and latent_out (conv1 mu half + normalise)."""
+    import movii_b200 as mv
+    g = torch.Generator().manual_seed(5)
+    T, H, W = 5, 6, 10
+    vid = (torch.rand(3, T, H, W, generator=g) * 2 - 1)
+    out = torch.full((2, H, W, 16), float("nan"), dtype=torch.float16, device=DEV)
+    mv.vae_video_in(vid.to(DEV), 2, 2, out)
+    exp = torch.zeros(2, H, W, 16, dtype=torch.float16)
+    exp[..., :3] = vid[:, 2:4].permute(1, 2, 3, 0).half()
+    assert torch.equal(out.cpu(), exp)
+    head = torch.randn(2, H, W, 32, generator=g).half()
+    w1, b1 = torch.randn(32, 32, generator=g) / math.sqrt(32), torch.randn(32, generator=g)
+    mean, std = torch.tensor(V.VAE_MEAN), torch.tensor(V.VAE_STD)
+    mu = torch.full((16, 3, H, W), float("nan"), device=DEV)
+    mv.vae_latent_out(head.to(DEV), w1.to(DEV), b1.to(DEV), mean.to(DEV), (1.0 / std).to(DEV), mu, 1)
+    ref = (head.float() @ w1.t() + b1)[..., :16]
+    ref = ((ref - mean) * (1.0 / std)).permute(3, 0, 1, 2)
+    assert torch.isnan(mu[:, 0]).all()                                         # frames outside [t0, t0+n) untouched
+    assert (mu[:, 1:].cpu() - ref).abs().max().item() <= 1e-5
