@@ -15,19 +15,28 @@ KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|MU
                  r"SYNCS|UCGABAR|ATOM|RED)\b")
 # (label, object file, regex on the demangled-ish function name, max loops to print)
 KERNELS = [
-    ("attention_fwd_k128 (default: fixed-reference softmax)", "attention_sm100.o", r"attention_fwd_k128_kernelILi0ELb0ELb0ELb1E", 4),
+    ("attention_fwd_k128 (default: fixed-reference softmax; also the Ulysses scatter epilogue)", "attention_sm100.o",
+     r"attention_fwd_k128_kernelILi0ELb0ELb0ELb1ELb0ELb0E", 4),
     ("attention_fwd (64-key variant)", "attention_sm100.o", r"attention_fwd_kernelILi1E", 3),
-    ("gemm_bf16 single CTA, residual epilogue", "gemm_sm100.o", r"gemm_bf16_kernelILi2ELi256E", 4),
-    ("gemm_bf16 single CTA, bf16+GELU epilogue", "gemm_sm100.o", r"gemm_bf16_kernelILi1ELi256E", 3),
-    ("gemm_bf16 CTA pair (cta_group::2), residual epilogue", "gemm_sm100.o", r"gemm_bf16_pair_kernelILi2E", 4),
-    ("conv_igemm BK=64 (WanVAE)", "vae_conv_sm100.o", r"conv_igemm_kernelILi64E", 4),
-    ("conv_igemm BK=32 (WanVAE, Cin=96)", "vae_conv_sm100.o", r"conv_igemm_kernelILi32E", 3),
+    ("gemm_bf16 single CTA, residual epilogue", "gemm_sm100.o", r"gemm_bf16_kernelILi2ELi256ELb0E", 4),
+    ("gemm_bf16 single CTA, bf16+GELU epilogue", "gemm_sm100.o", r"gemm_bf16_kernelILi1ELi256ELb0E", 3),
+    ("gemm_bf16 CTA pair (cta_group::2), residual epilogue", "gemm_sm100.o", r"gemm_bf16_pair_kernelILi2ELb0E", 4),
+    ("conv_igemm_pair BK=64 NT=1 (WanVAE stages A-C, cta_group::2)", "vae_conv_sm100.o", r"conv_igemm_pair_kernelILi64ELi1ELb0E", 4),
+    ("conv_igemm_pair BK=32 NT=2 (WanVAE stage D, cta_group::2)", "vae_conv_sm100.o", r"conv_igemm_pair_kernelILi32ELi2ELb0E", 4),
+    ("conv_igemm BK=64 (single CTA: 1x1x1 convs, strided encoder convs)", "vae_conv_sm100.o", r"conv_igemm_kernelILi64ELb0E", 4),
+    ("conv_igemm BK=32 (single CTA, Cin=96)", "vae_conv_sm100.o", r"conv_igemm_kernelILi32ELb0E", 3),
+    ("conv_igemm BK=16 (16-channel stems)", "vae_conv_sm100.o", r"conv_igemm_kernelILi16ELb0E", 3),
     ("rmsnorm_silu_cl (WanVAE)", "vae_conv_sm100.o", r"rmsnorm_silu_cl_kernelILi32ELi1E", 2),
-    ("softmax_rows (WanVAE attention)", "vae_conv_sm100.o", r"softmax_rows_kernel", 3),
+    ("softmax_rows_reg (WanVAE attention, register-resident row)", "vae_conv_sm100.o", r"softmax_rows_reg_kernel", 3),
+    ("vae_latent_in", "vae_conv_sm100.o", r"vae_latent_in_kernel", 1),
+    ("vae_video_in (encoder)", "vae_conv_sm100.o", r"vae_video_in_kernel", 1),
+    ("vae_latent_out (encoder)", "vae_conv_sm100.o", r"vae_latent_out_kernel", 1),
     ("ln_modulate", "rowops.o", r"ln_modulate_kernel", 2),
-    ("qkv_norm_rope (C = 5120)", "rowops.o", r"qkv_norm_rope_kernelILi20E", 2),
+    ("qkv_norm_rope (C = 5120; also the Ulysses p2p head scatter)", "rowops.o", r"qkv_norm_rope_kernelILi20E", 2),
     ("unipc_cfg_step", "rowops.o", r"unipc_cfg_step_kernel", 1),
+    ("modulation_table", "rowops.o", r"modulation_table_kernel", 1),
     ("head_unpatchify", "rowops.o", r"head_unpatchify_kernel", 3),
+    ("patchify", "rowops.o", r"\d+patchify_kernel", 1),
     ("linear_f32_vec", "rowops.o", r"linear_f32_vec_kernel", 2),
     ("sp_barrier", "p2p_sm100.o", r"sp_barrier_kernel", 1),
     ("t5_attention", "t5_sm100.o", r"t5_attention_kernel", 3),
