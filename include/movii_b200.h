@@ -217,7 +217,8 @@ int mv_vae_conv_fused(const void* in_cl, int in_T, int in_H, int in_W, int Cin, 
 
 /* Diagnostics only: 1 = route the tensor-bound convolutions to the CTA-pair kernel (cta_group::2, NT stacked tiles per
  * CTA, one A box per (dt, dw)), 0 = the single-CTA kernel, -1 = keep, -2 = back to the default (MV_CONV_PAIR or built-in). */
-int mv_vae_conv_config(int pair, int tiles_per_cta /* 0 auto, 1 | 2 | 4 */);
+int mv_vae_conv_config(int pair, int tiles_per_cta /* 0 auto, 1 | 2 | 4 */,
+                       int epi_regs /* fused norm epilogue: 1 = one TMEM pass, row in registers; 0 = two passes */);
 
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per voxel over channels (RMS_norm + nn.SiLU,
  * vae.py:39-54,194-199); channels-last fp16, in place allowed. */

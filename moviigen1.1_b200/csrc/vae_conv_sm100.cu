@@ -57,6 +57,7 @@ struct ConvParams {
   uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes (kps blocks each)
   const float* norm_gamma;      // fused RMS_norm + SiLU of the output row (needs BN == Cout): gamma [Cout] or null
   __half* norm_out;      // where silu(rms_norm(out)) goes (same addressing as out); `out` may then be null
+  int epi_regs;                 // fused norm epilogue: 1 = single TMEM pass, row kept in registers (BN = 96)
   int kps;                      // k-blocks per ring slot (3 for Cin = 96: one whole tap per slot, 6 MMAs per barrier trip)
   uint32_t a_block_bytes, b_block_bytes;
 };
@@ -167,10 +168,109 @@ __device__ __forceinline__ void conv_epilogue_fused(const ConvParams& p, uint32_
   }
 }
 
+// Hands an accumulator tile back to the MMA warp: local barrier (rel_cta < 0) or the barrier of CTA rel_cta of the pair.
+__device__ __forceinline__ void conv_release_tile(uint64_t* rel_bar, int rel_cta) {
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    if (rel_cta < 0) mbar_arrive(rel_bar);
+    else mbar_arrive_cluster(rel_bar, static_cast<uint32_t>(rel_cta));
+  }
+}
+
+// The same fused epilogue with ONE pass over TMEM for BN = 96 (stage D, where the two-pass epilogue costs the most): the
+// row is kept in 48 registers as packed fp16 — exactly the values that are stored, which is what the statistics are
+// defined on — so the accumulator buffer goes back to the MMA warp before the normalisation / SiLU / store pass
+// starts, TMEM is read once and bias / residual are applied once.  A real call (__noinline__): its register allocation
+// must not leak into the MMA-issue path of the calling kernel.
+struct FusedRowArgs {
+  const float* bias;
+  const __half* res;
+  __half* out;
+  __half* norm_out;
+  const float* gamma;
+  float sqrt_c;
+};
+
+__device__ __noinline__ void conv_epilogue_fused_regs96(const FusedRowArgs a, uint32_t taddr, int64_t off, bool ok,
+                                                        uint64_t* rel_bar, int rel_cta) {
+  constexpr int NCH = 3;
+  uint32_t h[NCH * 16];
+  float ss = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c = ch * 32;
+    uint32_t vc[32];
+    tmem_ld_x32(taddr + c, vc);
+    tc_wait_ld();
+    float f[32];
+    if (a.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c) + i);
+        f[4 * i + 0] = __uint_as_float(vc[4 * i + 0]) + b4.x;
+        f[4 * i + 1] = __uint_as_float(vc[4 * i + 1]) + b4.y;
+        f[4 * i + 2] = __uint_as_float(vc[4 * i + 2]) + b4.z;
+        f[4 * i + 3] = __uint_as_float(vc[4 * i + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(vc[i]);
+    }
+    if (a.res != nullptr && ok) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(a.res + off + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 q = r4[i];
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          f[8 * i + 2 * k] += f16_lo(u[k]);
+          f[8 * i + 2 * k + 1] += f16_hi(u[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t pk = pack_f16(f[2 * i], f[2 * i + 1]);
+      h[ch * 16 + i] = pk;
+      const float lo = f16_lo(pk), hi = f16_hi(pk);      // statistics of the value as it is stored
+      ss = fmaf(lo, lo, ss);
+      ss = fmaf(hi, hi, ss);
+    }
+  }
+  conv_release_tile(rel_bar, rel_cta);                   // the accumulator tile is free: the next MMAs may overwrite it
+  if (!ok) return;
+  if (a.out != nullptr) {
+    uint4* o4 = reinterpret_cast<uint4*>(a.out + off);
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) o4[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+  }
+  const float inv = a.sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+  uint4* n4 = reinterpret_cast<uint4*>(a.norm_out + off);
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma) + 2 * i);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma) + 2 * i + 1);
+    const float gg[8] = {g0.x * inv, g0.y * inv, g0.z * inv, g0.w * inv, g1.x * inv, g1.y * inv, g1.z * inv, g1.w * inv};
+    float y[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float u0 = f16_lo(h[4 * i + k]) * gg[2 * k], u1 = f16_hi(h[4 * i + k]) * gg[2 * k + 1];
+      y[2 * k] = __fdividef(u0, 1.f + __expf(-u0));
+      y[2 * k + 1] = __fdividef(u1, 1.f + __expf(-u1));
+    }
+    n4[i] = make_uint4(pack_f16(y[0], y[1]), pack_f16(y[2], y[3]), pack_f16(y[4], y[5]), pack_f16(y[6], y[7]));
+  }
+}
+
 // Epilogue of one accumulator tile for ONE output voxel (t, h, w) = this thread's TMEM lane: bias, residual, store —
 // or, with norm_out, the consumer's RMS_norm + SiLU fused in (two passes over the TMEM row).  taddr = this warp's lane
 // quadrant + the tile's first accumulator column.
-__device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t taddr, int n_blk, int t, int h, int w) {
+// (rel_bar, rel_cta) hand the accumulator tile back to the MMA warp (conv_release_tile) as soon as TMEM has been read for
+// the last time.
+__device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t taddr, int n_blk, int t, int h, int w,
+                                                   uint64_t* rel_bar, int rel_cta) {
   const bool ok = (h < p.H) && (w < p.W);
   int n0 = n_blk * p.BN;
   int64_t off = p.o_base + t * p.os_t + h * p.os_h + w * p.os_w;
@@ -180,6 +280,17 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
     off += p.nsplit_off;
   }
   if (p.norm_out != nullptr) {
+    if (p.epi_regs && p.BN == 96) {
+      FusedRowArgs a;
+      a.bias = p.bias;
+      a.res = p.res;
+      a.out = reinterpret_cast<__half*>(p.out);
+      a.norm_out = p.norm_out;
+      a.gamma = p.norm_gamma;
+      a.sqrt_c = sqrtf(static_cast<float>(p.Cout));
+      conv_epilogue_fused_regs96(a, taddr, off, ok, rel_bar, rel_cta);
+      return;
+    }
     if ((p.BN & 31) == 0) conv_epilogue_fused<true>(p, taddr, off, ok);
     else conv_epilogue_fused<false>(p, taddr, off, ok);
   } else
@@ -241,6 +352,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
       }
     }
   }
+  conv_release_tile(rel_bar, rel_cta);
 }
 
 template <int BK, bool HI>
@@ -369,10 +481,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256;
-      conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15), &tempty[as], -1);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -627,10 +736,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_after();
       for (int j = wset; j < NT; j += 2) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((buf * NT + j) * p.BN);
-        conv_epilogue_tile(p, taddr, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15));
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tempty[buf * NT + j], 0);
+        conv_epilogue_tile(p, taddr, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15), &tempty[buf * NT + j], 0);
       }
     }
   }
@@ -943,11 +1049,23 @@ bool conv_pair_enabled() {
 }
 }  // namespace
 
-extern "C" int mv_vae_conv_config(int pair, int tiles_per_cta) {
+constexpr int kDefaultConvEpiRegs = 0;   // fused norm epilogue: 1 = single TMEM pass with the row in registers
+int g_conv_epi = -1;
+static int conv_epi_regs() {
+  if (g_conv_epi < 0) {
+    const char* e = getenv("MV_CONV_EPI");
+    g_conv_epi = (e != nullptr && e[0] != 0) ? (atoi(e) != 0 ? 1 : 0) : kDefaultConvEpiRegs;
+  }
+  return g_conv_epi;
+}
+
+extern "C" int mv_vae_conv_config(int pair, int tiles_per_cta, int epi_regs) {
   if (pair >= 0) g_conv_pair = pair != 0 ? 1 : 0;
   else if (pair == -2) g_conv_pair = -1;   // back to MV_CONV_PAIR / the built-in default
   if (tiles_per_cta >= 0) g_conv_nt = tiles_per_cta;
   else if (tiles_per_cta == -2) g_conv_nt = -1;
+  if (epi_regs >= 0) g_conv_epi = epi_regs != 0 ? 1 : 0;
+  else if (epi_regs == -2) g_conv_epi = -1;
   return MV_OK;
 }
 
@@ -1081,6 +1199,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
         p.cout_real = cout_real;
         p.norm_gamma = norm_gamma;
         p.norm_out = reinterpret_cast<__half*>(norm_out);
+        p.epi_regs = conv_epi_regs();
         CUtensorMap tmA2, tmB2;
         {
           uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
@@ -1158,6 +1277,7 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   p.cout_real = cout_real;
   p.norm_gamma = norm_gamma;
   p.norm_out = reinterpret_cast<__half*>(norm_out);
+  p.epi_regs = conv_epi_regs();
   p.kps = (BK == 32 && p.kblocks_per_tap % 3 == 0) ? 3 : 1;
   p.a_block_bytes = (static_cast<uint32_t>(kConvBM * BK * 2) + 1023u) & ~1023u;
   p.b_block_bytes = (static_cast<uint32_t>(BN * BK * 2) + 1023u) & ~1023u;

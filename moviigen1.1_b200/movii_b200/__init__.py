@@ -66,7 +66,7 @@ _SIGNATURES = {
     "mv_attention_config": [_int, _int, _int, _int, _int, _int, _int],
     "mv_gemm_config": [_int],
     "mv_roles_config": [_int],
-    "mv_vae_conv_config": [_int, _int],
+    "mv_vae_conv_config": [_int, _int, _int],
     "mv_t5_attention": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _int, _int, _int, _int, _int, _ptr],
     "mv_t5_rmsnorm": [_ptr, _i64, _ptr, _ptr, _i64, _int, _int, _f32, _ptr],
     "mv_embed_gather": [_ptr, _i64, _i64, _ptr, _ptr, _i64, _int, _int, _ptr],
@@ -585,10 +585,11 @@ def gemm_config(pair=-1):
     _check(lib().mv_gemm_config(int(pair)), "mv_gemm_config")
 
 
-def vae_conv_config(pair=-1, tiles_per_cta=-1):
+def vae_conv_config(pair=-1, tiles_per_cta=-1, epi_regs=-1):
     """Diagnostics: pair 1 = CTA-pair convolution kernel for the tensor-bound WanVAE convs, 0 = single-CTA kernel;
-    tiles_per_cta 0 = automatic, 1 | 2 | 4 forced; -1 keeps, -2 restores the default."""
-    _check(lib().mv_vae_conv_config(int(pair), int(tiles_per_cta)), "mv_vae_conv_config")
+    tiles_per_cta 0 = automatic, 1 | 2 | 4 forced; epi_regs 1 = fused norm epilogue in one TMEM pass (row kept in
+    registers), 0 = two passes; -1 keeps, -2 restores the default."""
+    _check(lib().mv_vae_conv_config(int(pair), int(tiles_per_cta), int(epi_regs)), "mv_vae_conv_config")
 
 
 def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, skew=-1, wait_spin=-1, pack=-1):

@@ -48,7 +48,7 @@ def conv_kernel(request):
     import movii_b200 as mv
     mv.vae_conv_config(request.param)
     yield request.param
-    mv.vae_conv_config(-2, -2)
+    mv.vae_conv_config(-2, -2, -2)
 
 
 @pytest.mark.parametrize("case", [(1, 4, 6), (2, 5, 9), (3, 4, 6), (5, 4, 4)])
@@ -168,6 +168,40 @@ def test_vae_conv_pair_matches_single_cta(shape, mode, nt):
     assert (a - b).abs().max().item() <= 4e-3 * max(1.0, a.abs().max().item()), (a - b).abs().max().item()
     assert ((a - b).norm() / a.norm()).item() <= 5e-4
 
+
+@pytest.mark.parametrize("shape", [(3, 70, 40, 96, 96), (2, 33, 50, 192, 96), (2, 33, 50, 192, 192)])
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_vae_fused_epilogue_single_pass_matches_two_pass(shape, pair, with_res):
+    """The register-resident fused RMS_norm+SiLU epilogue (one TMEM pass, accumulator released before the normalisation)
+    against the two-pass one: same accumulators, same fp16-rounded row, same statistics order -> the raw output is
+    bit-identical and the normalised output differs by at most an fp16 rounding flip."""
+    import movii_b200 as mv
+    from wan.modules.vae import _Conv, _taps
+    T, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(7 * H + Co)
+    x = torch.randn(T + 2, H, W, Ci, generator=g).half().to(DEV)
+    wt = torch.randn(Co, Ci, 3, 3, 3, generator=g) / math.sqrt(27 * Ci)
+    c = _Conv(wt, 0.1 * torch.randn(Co, generator=g), _taps(3, 3, 3), DEV)
+    res = torch.randn(T, H, W, Co, generator=g).half().to(DEV) if with_res else None
+    gamma = (1 + 0.1 * torch.randn(Co, generator=g)).to(DEV)
+    outs = []
+    for epi in (0, 1):
+        mv.vae_conv_config(pair, 0, epi)
+        try:
+            raw = torch.full((T, H, W, Co), float("nan"), dtype=torch.float16, device=DEV)
+            nrm = torch.full((T, H, W, Co), float("nan"), dtype=torch.float16, device=DEV)
+            mv.vae_conv_fused(x, c, raw if with_res else None, gamma, nrm, res=res, o_base=0, os_t=H * W * Co,
+                              os_h=W * Co, os_w=Co, t_off=2)
+            torch.cuda.synchronize()
+        finally:
+            mv.vae_conv_config(-2, -2, -2)
+        outs.append((raw.float(), nrm.float()))
+    (raw0, n0), (raw1, n1) = outs
+    assert torch.isfinite(n1).all()
+    if with_res:
+        assert torch.equal(raw0, raw1)
+    assert (n0 - n1).abs().max().item() <= 2e-3 * max(1.0, n0.abs().max().item()), (n0 - n1).abs().max().item()
 
 # ---- encoder (SURVEY.md §8f-4) ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", [(1, 16, 24), (5, 24, 40), (9, 16, 16), (13, 32, 16)])

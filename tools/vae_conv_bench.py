@@ -82,9 +82,14 @@ def main():
             ms = timeit(lambda: mv.vae_conv(x, c, out, res=res, **kw))
             rec[label + "_tflops"] = round(fl / ms / 1e9, 1)
             if Co <= 256:
-                ms2 = timeit(lambda: mv.vae_conv_fused(x, c, None, gamma, nout, **kw))
-                rec[label + "_fused_tflops"] = round(fl / ms2 / 1e9, 1)
-        mv.vae_conv_config(-2, -2)
+                for epi in (0, 1):
+                    mv.vae_conv_config(epi_regs=epi)
+                    tag = "_fused" + ("_regs" if epi else "")
+                    ms2 = timeit(lambda: mv.vae_conv_fused(x, c, None, gamma, nout, **kw))
+                    rec[label + tag + "_tflops"] = round(fl / ms2 / 1e9, 1)
+                    ms3 = timeit(lambda: mv.vae_conv_fused(x, c, out, gamma, nout, res=res, **kw))
+                    rec[label + tag + "_res_tflops"] = round(fl / ms3 / 1e9, 1)
+        mv.vae_conv_config(-2, -2, -2)
         print(json.dumps(rec), flush=True)
         del x, out, res
 
