@@ -388,11 +388,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 // fp16 (saturating: a value beyond +-65504 is stored as the largest finite half instead of inf)
 __device__ __forceinline__ float f16_sat(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+// one F2FP.SATFINITE.F16.F32.PACK_AB: round-to-nearest-even with the saturation built in (NaN stays NaN)
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 v = __floats2half2_rn(f16_sat(lo), f16_sat(hi));  // .x = lo (low 16 bits)
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
 }
-__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(f16_sat(x))); }
+__device__ __forceinline__ float f16_round(float x) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return __half2float(__ushort_as_half(h));
+}
 __device__ __forceinline__ float f16_lo(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xffffu))); }
 __device__ __forceinline__ float f16_hi(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }

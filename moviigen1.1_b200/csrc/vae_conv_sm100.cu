@@ -192,9 +192,9 @@ struct FusedRowArgs {
   float sqrt_c;
 };
 
-__device__ __noinline__ void conv_epilogue_fused_regs96(const FusedRowArgs a, uint32_t taddr, int64_t off, bool ok,
-                                                        uint64_t* rel_bar, int rel_cta) {
-  constexpr int NCH = 3;
+template <int NCH>
+__device__ __noinline__ void conv_epilogue_fused_regs(const FusedRowArgs a, uint32_t taddr, int64_t off, bool ok,
+                                                      uint64_t* rel_bar, int rel_cta) {
   uint32_t h[NCH * 16];
   float ss = 0.f;
 #pragma unroll
@@ -280,7 +280,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
     off += p.nsplit_off;
   }
   if (p.norm_out != nullptr) {
-    if (p.epi_regs && p.BN == 96) {
+    if (p.epi_regs && p.BN == 96) {    // (192-channel rows would need 96 + 64 registers: ptxas spills ~900 B — measured, dropped)
       FusedRowArgs a;
       a.bias = p.bias;
       a.res = p.res;
@@ -288,7 +288,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
       a.norm_out = p.norm_out;
       a.gamma = p.norm_gamma;
       a.sqrt_c = sqrtf(static_cast<float>(p.Cout));
-      conv_epilogue_fused_regs96(a, taddr, off, ok, rel_bar, rel_cta);
+      conv_epilogue_fused_regs<3>(a, taddr, off, ok, rel_bar, rel_cta);
       return;
     }
     if ((p.BN & 31) == 0) conv_epilogue_fused<true>(p, taddr, off, ok);
@@ -302,10 +302,21 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
     if (ok) {
       if (p.out_mode == 0) {
         float f[32];
+        if (ncols == 32 && p.bias != nullptr) {       // whole chunk (n0, c multiples of 16/32, Cout % 16 == 0): vector loads
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float b = (p.bias != nullptr && i < ncols && n0 + c + i < p.Cout) ? __ldg(p.bias + n0 + c + i) : 0.f;
-          f[i] = __uint_as_float(v[i]) + b;
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + i);
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float b = (p.bias != nullptr && i < ncols && n0 + c + i < p.Cout) ? __ldg(p.bias + n0 + c + i) : 0.f;
+            f[i] = __uint_as_float(v[i]) + b;
+          }
         }
         __half* o = reinterpret_cast<__half*>(p.out) + off + nb + c;
         if (p.res != nullptr) {
@@ -878,8 +889,8 @@ vae_video_in_kernel(const float* __restrict__ video, int64_t chan_stride, int64_
        v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float r = video[base + v], g = video[chan_stride + base + v], b = video[2 * chan_stride + base + v];
     uint4 lo;
-    lo.x = pack_f16(f16_sat(r), f16_sat(g));
-    lo.y = pack_f16(f16_sat(b), 0.f);
+    lo.x = pack_f16(r, g);
+    lo.y = pack_f16(b, 0.f);
     lo.z = 0u;
     lo.w = 0u;
     out[2 * v] = lo;
@@ -1049,7 +1060,8 @@ bool conv_pair_enabled() {
 }
 }  // namespace
 
-constexpr int kDefaultConvEpiRegs = 0;   // fused norm epilogue: 1 = single TMEM pass with the row in registers
+constexpr int kDefaultConvEpiRegs = 1;   // fused norm epilogue: 1 = single TMEM pass with the row in registers (stage D fused
+                                         // conv 894 -> 1193 TF/s, profiles/r02_vae_conv_epilogue_ab.jsonl); MV_CONV_EPI=0 = two passes
 int g_conv_epi = -1;
 static int conv_epi_regs() {
   if (g_conv_epi < 0) {

@@ -240,6 +240,8 @@ class VaeEngine:
         # 16 frames instead of 81).
         self.chunk = max(1, int(os.environ.get("MOVII_VAE_CHUNK", "4")))
         self.cache = {}
+        # A/B switch (tools/vae_bench.py): 0 = the block's last conv does not emit the consumer's norm (stand-alone pass)
+        self.fuse_c6 = os.environ.get("MOVII_VAE_FUSE_C6", "1") != "0"
         self.model = model
         self.enc = None              # encoder plan, packed on the first encode()
 
@@ -313,7 +315,7 @@ class VaeEngine:
             self.normsilu(y[ky:], p["g3"])
         del a
         self.commit(key + ".c6", y)
-        if nxt is not None and self._fusable(c6):
+        if nxt is not None and self._fusable(c6) and self.fuse_c6:
             gamma_n, key_n = nxt
             an, kn = self.halo_buffer(key_n, n, H, W, c6.cout)
             out = torch.empty(n, H, W, c6.cout, dtype=F16, device=self.device)
