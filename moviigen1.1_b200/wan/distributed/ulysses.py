@@ -40,6 +40,10 @@ class UlyssesGroup:
         self.mode = mode or os.environ.get("MOVII_SP_MODE", "p2p")
         self._p2p = {}
         self.epoch = 0
+        # p2p mode: the QKV GEMM runs as three column-slab GEMMs and the NVLink scatter of q (k) is issued on a side
+        # stream while the k (v) GEMM runs — MOVII_SP_PIPELINE=0 restores one GEMM + one scatter launch (A/B)
+        self.pipeline = os.environ.get("MOVII_SP_PIPELINE", "1") != "0"
+        self._side = None
 
     def buffers(self, rows, dim, device, dtype=torch.bfloat16):
         key = (rows, dim, str(device))
@@ -108,6 +112,12 @@ class UlyssesGroup:
         self._p2p[key] = st
         return st
 
+    def side_stream(self, device):
+        """(side stream, three reusable events) for the pipelined q / k / v scatter."""
+        if self._side is None:
+            self._side = (torch.cuda.Stream(device=device), [torch.cuda.Event() for _ in range(3)])
+        return self._side
+
     def p2p_barrier(self, mv, st):
         self.epoch += 1
         mv.sp_barrier(st["flags"], st["local_flags"], self.rank, self.world, self.epoch)
@@ -140,8 +150,10 @@ def token_range(seq_len, world, rank):
     return rank * n, n
 
 
-def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, attend=None):
-    """Self-attention core for the local `rows` tokens whose fused QKV GEMM output sits in ws.qkv.
+def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, attend=None, qkv_gemm=None):
+    """Self-attention core for the local `rows` tokens.  qkv_gemm=None: the fused QKV GEMM output already sits in ws.qkv;
+    otherwise qkv_gemm(i) computes column slab i (0 = q, 1 = k, 2 = v) and qkv_gemm(None) all of it — which lets the p2p
+    mode hide the NVLink scatter of q and k behind the GEMMs of k and v.
 
     Leaves the attention output as K-split slabs in the returned tensor [P, rows, C/P] (consumed by
     mv.gemm_ksplit).  `prepare` / `attend` are injection points for the gloo CPU tests of this choreography;
@@ -154,10 +166,30 @@ def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, att
         st = grp.p2p_buffers(mv, rows, C, ws.qkv.device)
     if grp.mode == "p2p" and prepare is None and attend is None:
         qkv = ws.qkv[:rows]
-        # ONE pass over the local QKV rows: q/k RMSNorm + RoPE, and the head groups of q, k and v stored straight
-        # into slab `rank` of every destination's receive buffers
-        mv.qkv_norm_rope(qkv, bw.g_q, bw.g_k, cs, 128, bw.eps, dst=(st["tab"][0], st["tab"][1], st["tab"][2]),
-                         n_dst=P, src_slot=grp.rank)
+        if qkv_gemm is not None and grp.pipeline:
+            # q GEMM | k GEMM + scatter(q) | v GEMM + scatter(k) | scatter(v): the scatter kernels (norm + RoPE + peer
+            # stores, NVLink-bound) run on a side stream next to the compute-bound GEMMs of the following slab
+            main = torch.cuda.current_stream()
+            side, ev = grp.side_stream(qkv.device)
+            for i in range(3):
+                qkv_gemm(i)
+                slab = qkv[:, i * C:(i + 1) * C]
+                if i < 2:
+                    ev[i].record(main)
+                    side.wait_event(ev[i])
+                    with torch.cuda.stream(side):
+                        mv.qkv_prepare_p2p(slab, (bw.g_q, bw.g_k)[i], cs, st["tab"][i], grp.rank, P, 128, bw.eps)
+                else:
+                    mv.qkv_prepare_p2p(slab, None, None, st["tab"][2], grp.rank, P, 128, bw.eps)
+            ev[2].record(side)
+            main.wait_event(ev[2])
+        else:
+            if qkv_gemm is not None:
+                qkv_gemm(None)
+            # ONE pass over the local QKV rows: q/k RMSNorm + RoPE, and the head groups of q, k and v stored straight
+            # into slab `rank` of every destination's receive buffers
+            mv.qkv_norm_rope(qkv, bw.g_q, bw.g_k, cs, 128, bw.eps, dst=(st["tab"][0], st["tab"][1], st["tab"][2]),
+                             n_dst=P, src_slot=grp.rank)
         grp.p2p_barrier(mv, st)                    # all q/k/v slabs complete everywhere
         L = P * rows
         hd = C // bw.num_heads
@@ -167,6 +199,8 @@ def sp_self_attention(mv, grp, ws, rows, bw, cs, kv_len_total, prepare=None, att
         mv.attention_scatter(q, k, v, st["tab"][3], P, grp.rank, rows, Hl * hd)
         grp.p2p_barrier(mv, st)                    # all o slabs complete; also fences q/k/v reuse by the next layer
         return st["o_r"]
+    if qkv_gemm is not None:
+        qkv_gemm(None)
     b = grp.buffers(rows, C, ws.qkv.device, ws.qkv.dtype)
     qkv = ws.qkv[:rows]
     if prepare is None:

@@ -126,14 +126,21 @@ def block_forward(bw, ws, rows, e, cs, ctx, kv_rows, first_block=False, sp=None)
         raise NotImplementedError("qk_norm=False is not a configuration the 14B model uses")
     # --- self-attention: x += o(attn(rope(rms(q)), rope(rms(k)), v)) * e2          model.py:298-302
     mv.ln_modulate(x, h, shift=e[0], scale=e[1], eps=eps, round_ln=first_block)
-    mv.gemm(h, bw.w_qkv, bw.b_qkv, qkv, mv.MV_EPI_BF16)
     if sp is None or sp.world == 1:
+        mv.gemm(h, bw.w_qkv, bw.b_qkv, qkv, mv.MV_EPI_BF16)
         mv.qkv_norm_rope(qkv, bw.g_q, bw.g_k, cs, 128, eps)      # q and k in one launch
         self_attention_core(ws, rows, kv_rows, nh)
         mv.gemm(attn, bw.w_o, bw.b_o, x, mv.MV_EPI_RESID_F32, gate=e[2])
     else:
         from ..distributed.ulysses import sp_self_attention
-        o_slabs = sp_self_attention(mv, sp, ws, rows, bw, cs, kv_rows)
+
+        def qkv_gemm(i):      # column slab i of the fused QKV projection (same tiles, same bits as the single launch)
+            if i is None:
+                mv.gemm(h, bw.w_qkv, bw.b_qkv, qkv, mv.MV_EPI_BF16)
+            else:
+                b = None if bw.b_qkv is None else bw.b_qkv[i * C:(i + 1) * C]
+                mv.gemm(h, bw.w_qkv[i * C:(i + 1) * C], b, qkv[:, i * C:(i + 1) * C], mv.MV_EPI_BF16)
+        o_slabs = sp_self_attention(mv, sp, ws, rows, bw, cs, kv_rows, qkv_gemm=qkv_gemm)
         mv.gemm_ksplit(o_slabs, bw.w_o, bw.b_o, x, mv.MV_EPI_RESID_F32, gate=e[2])
     # --- cross-attention: x += o(attn(rms(q(norm3 x)), rms(k(ctx)), v(ctx)))        model.py:306,159-181
     if bw.n3_w is not None:

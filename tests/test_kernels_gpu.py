@@ -322,6 +322,29 @@ def test_qkv_norm_rope_fused(mv, M, C, hd, P):
             assert torch.isnan(other.float()).all()                          # nothing outside the addressed slab
 
 
+def test_qkv_prepare_p2p_per_slab_equals_fused_launch(mv):
+    """The pipelined Ulysses exchange scatters q, k and v with one mv_qkv_prepare_p2p launch per column slab (so that each
+    can run next to the following slab's GEMM); the three launches must write the same bits as the single fused
+    mv_qkv_norm_rope launch."""
+    M, C, hd, P, slot = 333, 1024, 128, 4, 2
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(M, 3 * C, generator=g) * 2).bfloat16().to(DEV)
+    gq, gk = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV), (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    ang = O.rope_table((M, 1, 1), hd, M)
+    cs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(DEV)
+    mk = lambda: {n: torch.full((P, P, M, C // P), float("nan"), dtype=torch.bfloat16, device=DEV) for n in "qkv"}  # noqa: E731
+    fused, slabs = mk(), mk()
+    tabs = {n: mv.ptr_table([fused[n][d].data_ptr() for d in range(P)]) for n in "qkv"}
+    mv.qkv_norm_rope(x, gq, gk, cs, hd, 1e-6, dst=(tabs["q"], tabs["k"], tabs["v"]), n_dst=P, src_slot=slot)
+    for i, (n, gain, c) in enumerate((("q", gq, cs), ("k", gk, cs), ("v", None, None))):
+        tab = mv.ptr_table([slabs[n][d].data_ptr() for d in range(P)])
+        mv.qkv_prepare_p2p(x[:, i * C:(i + 1) * C], gain, c, tab, slot, P, hd, 1e-6)
+    torch.cuda.synchronize()
+    for n in "qkv":
+        a, b = fused[n].view(torch.int16), slabs[n].view(torch.int16)
+        assert torch.equal(a, b), n
+
+
 def test_modulation_table(mv):
     g = torch.Generator().manual_seed(4)
     mods, e0 = torch.randn(5, 6, 384, generator=g), torch.randn(6 * 384, generator=g)
