@@ -40,9 +40,11 @@ class UlyssesGroup:
         self.mode = mode or os.environ.get("MOVII_SP_MODE", "p2p")
         self._p2p = {}
         self.epoch = 0
-        # p2p mode: the QKV GEMM runs as three column-slab GEMMs and the NVLink scatter of q (k) is issued on a side
-        # stream while the k (v) GEMM runs — MOVII_SP_PIPELINE=0 restores one GEMM + one scatter launch (A/B)
-        self.pipeline = os.environ.get("MOVII_SP_PIPELINE", "1") != "0"
+        # p2p mode, MOVII_SP_PIPELINE=1: the QKV GEMM runs as three column-slab GEMMs and the NVLink scatter of q (k) is
+        # issued on a side stream while the k (v) GEMM runs.  Bit-identical; measured at N = 2: non-attention time -8 ms,
+        # attention +16 ms per step (the step is energy-bound: hiding a low-power phase lowers the clock of what
+        # follows) -> off by default (profiles/r02_ab_sp_pipeline_n2.jsonl)
+        self.pipeline = os.environ.get("MOVII_SP_PIPELINE", "0") == "1"
         self._side = None
 
     def buffers(self, rows, dim, device, dtype=torch.bfloat16):
