@@ -192,9 +192,12 @@ struct FusedRowArgs {
   float sqrt_c;
 };
 
+// Column split (pair kernel, one tile per CTA): the two epilogue warp sets each take half of a 192-channel row; the
+// partial sums of squares meet in shared memory (ss_mine / ss_other, named barrier 1 over the 8 epilogue warps).
 template <int NCH>
 __device__ __noinline__ void conv_epilogue_fused_regs(const FusedRowArgs a, uint32_t taddr, int64_t off, bool ok,
-                                                      uint64_t* rel_bar, int rel_cta) {
+                                                      uint64_t* rel_bar, int rel_cta, float* ss_mine,
+                                                      const float* ss_other) {
   uint32_t h[NCH * 16];
   float ss = 0.f;
 #pragma unroll
@@ -240,6 +243,11 @@ __device__ __noinline__ void conv_epilogue_fused_regs(const FusedRowArgs a, uint
     }
   }
   conv_release_tile(rel_bar, rel_cta);                   // the accumulator tile is free: the next MMAs may overwrite it
+  if (ss_mine != nullptr) {                              // the other half of the row lives in the other warp set
+    *ss_mine = ss;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    ss += *ss_other;
+  }
   if (!ok) return;
   if (a.out != nullptr) {
     uint4* o4 = reinterpret_cast<uint4*>(a.out + off);
@@ -264,13 +272,31 @@ __device__ __noinline__ void conv_epilogue_fused_regs(const FusedRowArgs a, uint
   }
 }
 
+// The residual row of this thread's voxel is last-touched a whole conv ago (DRAM): ask for it while the tile's MMAs are
+// still running, so that the epilogue's loads find it in L2 instead of serialising three DRAM round trips per tile
+// (ncu: tensor pipe 63 % with the residual + two-output epilogue vs 75 % without, at a HIGHER clock).
+__device__ __forceinline__ void conv_prefetch_res(const ConvParams& p, int n_blk, int t, int h, int w, int c0, int ncol) {
+  if (p.res == nullptr || h >= p.H || w >= p.W) return;
+  int n0 = n_blk * p.BN;
+  int64_t off = p.o_base + t * p.os_t + h * p.os_h + w * p.os_w;
+  if (p.nsplit > 0 && n0 >= p.nsplit) {
+    n0 -= p.nsplit;
+    off += p.nsplit_off;
+  }
+  const char* a = reinterpret_cast<const char*>(p.res + off + (p.norm_out != nullptr ? 0 : n0) + c0);
+  for (int b = 0; b < ncol * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
+}
+
 // Epilogue of one accumulator tile for ONE output voxel (t, h, w) = this thread's TMEM lane: bias, residual, store —
 // or, with norm_out, the consumer's RMS_norm + SiLU fused in (two passes over the TMEM row).  taddr = this warp's lane
 // quadrant + the tile's first accumulator column.
 // (rel_bar, rel_cta) hand the accumulator tile back to the MMA warp (conv_release_tile) as soon as TMEM has been read for
 // the last time.
+// [c0, c0 + ncol) = the accumulator columns this thread drains (the whole tile, or one half of it when the two warp sets
+// of the pair kernel share a tile; then ss_mine / ss_other carry the fused norm's partial statistics).
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t taddr, int n_blk, int t, int h, int w,
-                                                   uint64_t* rel_bar, int rel_cta) {
+                                                   uint64_t* rel_bar, int rel_cta, int c0, int ncol, float* ss_mine,
+                                                   const float* ss_other) {
   const bool ok = (h < p.H) && (w < p.W);
   int n0 = n_blk * p.BN;
   int64_t off = p.o_base + t * p.os_t + h * p.os_h + w * p.os_w;
@@ -280,21 +306,22 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
     off += p.nsplit_off;
   }
   if (p.norm_out != nullptr) {
-    if (p.epi_regs && p.BN == 96) {    // (192-channel rows would need 96 + 64 registers: ptxas spills ~900 B — measured, dropped)
+    if (p.epi_regs && ncol == 96) {    // a 96-channel row, or half of a 192-channel one (a whole 192-channel row would need
+                                       // 96 + 64 registers: ptxas spills ~900 B — measured, dropped)
       FusedRowArgs a;
-      a.bias = p.bias;
+      a.bias = p.bias != nullptr ? p.bias + c0 : nullptr;
       a.res = p.res;
       a.out = reinterpret_cast<__half*>(p.out);
       a.norm_out = p.norm_out;
-      a.gamma = p.norm_gamma;
+      a.gamma = p.norm_gamma + c0;
       a.sqrt_c = sqrtf(static_cast<float>(p.Cout));
-      conv_epilogue_fused_regs<3>(a, taddr, off, ok, rel_bar, rel_cta);
+      conv_epilogue_fused_regs<3>(a, taddr + c0, off + c0, ok, rel_bar, rel_cta, ss_mine, ss_other);
       return;
     }
     if ((p.BN & 31) == 0) conv_epilogue_fused<true>(p, taddr, off, ok);
     else conv_epilogue_fused<false>(p, taddr, off, ok);
   } else
-  for (int c = 0; c < p.BN; c += 32) {   // BN multiple of 16: last chunk may be half valid
+  for (int c = c0; c < c0 + ncol; c += 32) {   // BN multiple of 16: last chunk may be half valid
     uint32_t v[32];
     tmem_ld_x32(taddr + c, v);
     tc_wait_ld();
@@ -489,10 +516,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int n_blk, t, h0, w0;
       decode(tile, n_blk, t, h0, w0);
+      conv_prefetch_res(p, n_blk, t, h0 + (r >> 4), w0 + (r & 15), 0, p.BN);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256;
-      conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15), &tempty[as], -1);
+      conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15), &tempty[as], -1, 0, p.BN, nullptr, nullptr);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -528,7 +556,7 @@ constexpr int kDefaultConvPair = 1;   // measured: 1080P decode 47 -> 73 fps (pr
 constexpr int kConv2MaxGroups = 9;
 constexpr int kConv2MaxStages = 6;
 constexpr uint32_t kConv2RingBytes = 216 * 1024;
-constexpr uint32_t kConv2Smem = kConv2RingBytes + 1024 + 512;
+constexpr uint32_t kConv2Smem = kConv2RingBytes + 1024 + 512 + 2048;   // + [2][2][128] floats: row statistics of a split tile
 
 struct Conv2Params {
   ConvParams c;
@@ -539,6 +567,7 @@ struct Conv2Params {
   int dh_min, box_h;                        // A box: h from (tile origin + dh_min), box_h = 8 NT + dh_max - dh_min rows
   uint32_t a_box_bytes, b_slab_bytes, stage_bytes;   // 1024-aligned
   int stages, nbuf;
+  int split_cols;                           // NT = 1: both epilogue warp sets drain the one tile, half of its columns each
   int regular;                              // n > 0: every group = n vertical taps dh = dh_min, dh_min + 1, ... in order
   int sup_h, sup_w, num_super;              // super-tiles (pair = 16 NT x 16 voxels) per frame in h / w; total incl. t, n
 };
@@ -581,6 +610,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tfull = bars + 2 * kConv2MaxStages;           // [nbuf], both CTAs (multicast commit)
   uint64_t* tempty = bars + 2 * kConv2MaxStages + 2;      // [nbuf][NT], leader only: 4 warps x 2 CTAs arrive
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConv2MaxStages + 2 + 2 * NT);
+  float* ssx = reinterpret_cast<float*>(smem + kConv2RingBytes + 512);   // [parity][warp set][row]
+  const bool split = (NT == 1) && q.split_cols != 0;
 
   const int pw = threadIdx.x >> 5;                      // physical warp: TMEM lane quadrant = pw & 3
   const int warp = HI ? (pw + 2) % 10 : pw;             // role id: 0 TMA, 1 MMA, 2-9 epilogue (HI: roles on warps 8, 9)
@@ -601,7 +632,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(&tfull[i], 1);
-    for (int i = 0; i < 2 * NT; ++i) mbar_init(&tempty[i], 8);
+    for (int i = 0; i < 2 * NT; ++i) mbar_init(&tempty[i], split ? 16 : 8);   // arriving warps: 4 (8 if split) x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
@@ -743,11 +774,24 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t use = static_cast<uint32_t>(it / nbuf);
       int n_blk, t, h0, w0;
       decode(st, n_blk, t, h0, w0);
+      if (split) conv_prefetch_res(p, n_blk, t, h0 + (r >> 4), w0 + (r & 15), wset * (p.BN >> 1), p.BN >> 1);
+      else
+        for (int j = wset; j < NT; j += 2) conv_prefetch_res(p, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15), 0, p.BN);
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after();
+      if (split) {
+        const int half = p.BN >> 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
+        float* mine = ssx + ((it & 1) * 2 + wset) * 128 + r;
+        const float* other = ssx + ((it & 1) * 2 + (wset ^ 1)) * 128 + r;
+        conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15), &tempty[buf], 0, wset * half, half,
+                           p.norm_out != nullptr ? mine : nullptr, other);
+        continue;
+      }
       for (int j = wset; j < NT; j += 2) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((buf * NT + j) * p.BN);
-        conv_epilogue_tile(p, taddr, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15), &tempty[buf * NT + j], 0);
+        conv_epilogue_tile(p, taddr, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15), &tempty[buf * NT + j], 0, 0,
+                           p.BN, nullptr, nullptr);
       }
     }
   }
@@ -1071,6 +1115,16 @@ static int conv_epi_regs() {
   return g_conv_epi;
 }
 
+constexpr int kDefaultConvSplit = 1;
+static int conv_split_enabled() {        // MV_CONV_SPLIT=0: A/B against one warp set per tile
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MV_CONV_SPLIT");
+    v = (e != nullptr && e[0] != 0) ? (atoi(e) != 0 ? 1 : 0) : kDefaultConvSplit;
+  }
+  return v;
+}
+
 extern "C" int mv_vae_conv_config(int pair, int tiles_per_cta, int epi_regs) {
   if (pair >= 0) g_conv_pair = pair != 0 ? 1 : 0;
   else if (pair == -2) g_conv_pair = -1;   // back to MV_CONV_PAIR / the built-in default
@@ -1180,6 +1234,10 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
       q.stages = static_cast<int>(kConv2RingBytes / q.stage_bytes);
       if (q.stages > kConv2MaxStages) q.stages = kConv2MaxStages;
       q.nbuf = (2 * nt * BN <= 512) ? 2 : 1;
+      // one tile per CTA leaves the second epilogue warp set idle: let both drain the tile, half of the columns each
+      // (plain epilogue: any BN that halves into 32-column chunks; fused norm: 192 = 2 x 96 register-resident halves)
+      q.split_cols = (nt == 1 && BN % 64 == 0 && out_mode == 0 && conv_split_enabled() &&
+                      (norm_out == nullptr || (conv_epi_regs() && BN == 192))) ? 1 : 0;
       q.sup_h = (out_H + 2 * nt * kConvTH - 1) / (2 * nt * kConvTH);
       q.sup_w = (out_W + kConvTW - 1) / kConvTW;
       const int num_n = Cout / BN;

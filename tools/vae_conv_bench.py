@@ -89,6 +89,11 @@ def main():
                     rec[label + tag + "_tflops"] = round(fl / ms2 / 1e9, 1)
                     ms3 = timeit(lambda: mv.vae_conv_fused(x, c, out, gamma, nout, res=res, **kw))
                     rec[label + tag + "_res_tflops"] = round(fl / ms3 / 1e9, 1)
+                    if os.environ.get("CONV_SPLIT"):      # which part of the fused+res epilogue costs: residual load or second store
+                        ms4 = timeit(lambda: mv.vae_conv_fused(x, c, None, gamma, nout, res=res, **kw))
+                        rec[label + tag + "_resonly_tflops"] = round(fl / ms4 / 1e9, 1)
+                        ms5 = timeit(lambda: mv.vae_conv_fused(x, c, out, gamma, nout, **kw))
+                        rec[label + tag + "_rawonly_tflops"] = round(fl / ms5 / 1e9, 1)
         mv.vae_conv_config(-2, -2, -2)
         print(json.dumps(rec), flush=True)
         del x, out, res
