@@ -250,6 +250,15 @@ int mv_vae_video_in(const float* video, int T_total, int t0, int n, int H, int W
 int mv_vae_latent_out(const void* head_cl, const float* W1, const float* b1, const float* mean, const float* inv_std,
                       float* mu, int Z, int64_t nvox, int64_t mu_plane, int64_t mu_off, mv_stream_t stream);
 
+/* Second half of the decoder's head conv (96 -> 3, 3x3x3, vae.py:420-421 + the clamp of :660-661) computed as
+ *   out[co, v] = clamp(bias[co] + sum_tap D[v + tap][4*tap + co], -1, 1),
+ * where D [frames, H, W, 112] fp16 = one 1x1x1 mv_vae_conv of the normalised input with the 27 x (3 + 1 pad) tap-major weight
+ * matrix.  d_cur: D of this chunk's n frames; d_prev: D of the kprev (<= 2) frames before it (NULL / 0 at the start of the
+ * sequence); bias3_host: the three biases (HOST pointer); video fp32 [3][plane], frame t of the chunk lands at
+ * frame_off + t*H*W. */
+int mv_vae_head_gather(const void* d_cur, const void* d_prev, int kprev, int n, int H, int W, const float* bias3_host,
+                       float* video, int64_t plane, int64_t frame_off, mv_stream_t stream);
+
 /* P_f16[m, :N] = softmax(S[m, :N] * scale) (fp32 in, fp16 out): the softmax of the VAE's single-head attention between the
  * two tcgen05 GEMMs (vae.py:246-257). */
 int mv_softmax_rows(const float* S, int64_t lds, void* P_f16, int64_t ldp, int M, int N, float scale,

@@ -971,6 +971,54 @@ vae_latent_out_kernel(const __half* __restrict__ head, const float* __restrict__
 }
 
 // --------------------------------------------------------------------------------------------
+// Head conv (96 -> 3, 3x3x3) without 162 sixteen-column MMAs per voxel tile: the conv is linear, so
+//   out[co, v] = bias[co] + sum_tap D[v + tap][tap][co]      with      D[u][tap][co] = in[u, :] . W[co][tap][:]
+// D is ONE 1x1x1 convolution 96 -> 27 taps x 4 (3 real channels + pad) = 112 columns on the implicit-GEMM kernel; this
+// kernel is the gather: per output voxel 27 8-byte loads of its neighbours' partial sums (fp16, fp32 accumulation, fixed
+// order), bias, clamp(-1, 1), fp32 channel-first store (vae.py:660-661).  Frames before the chunk come from d_prev
+// (the last kprev <= 2 frames of D of the previous chunk); frames before the sequence and voxels outside the image
+// contribute zero (causal / spatial zero padding, vae.py:17-36).
+// --------------------------------------------------------------------------------------------
+constexpr int kHeadLd = 112;
+__global__ void __launch_bounds__(256)
+vae_head_gather_kernel(const __half* __restrict__ d_cur, const __half* __restrict__ d_prev, int kprev, int H, int W,
+                       float b0, float b1, float b2, float* __restrict__ video, int64_t plane, int64_t frame_off) {
+  const int w = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int h = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int t = blockIdx.z;
+  if (w >= W || h >= H) return;
+  const int64_t fvox = static_cast<int64_t>(H) * W;
+  float a0 = b0, a1 = b1, a2 = b2;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int tt = t + it - 2;
+    const __half* frame;
+    if (tt >= 0) frame = d_cur + tt * fvox * kHeadLd;
+    else if (kprev + tt >= 0) frame = d_prev + (kprev + tt) * fvox * kHeadLd;
+    else continue;
+#pragma unroll
+    for (int ih = 0; ih < 3; ++ih) {
+      const int hh = h + ih - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int iw = 0; iw < 3; ++iw) {
+        const int ww = w + iw - 1;
+        if (ww < 0 || ww >= W) continue;
+        const int tap = (it * 3 + ih) * 3 + iw;
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(frame + (static_cast<int64_t>(hh) * W + ww) * kHeadLd + tap * 4));
+        a0 += f16_lo(q.x);
+        a1 += f16_hi(q.x);
+        a2 += f16_lo(q.y);
+      }
+    }
+  }
+  const int64_t pos = frame_off + (static_cast<int64_t>(t) * H + h) * W + w;
+  video[pos] = fminf(1.f, fmaxf(-1.f, a0));
+  video[plane + pos] = fminf(1.f, fmaxf(-1.f, a1));
+  video[2 * plane + pos] = fminf(1.f, fmaxf(-1.f, a2));
+}
+
+// --------------------------------------------------------------------------------------------
 // Row softmax for the VAE's single-head attention: P = softmax(S * scale), S fp32 [M, N] -> P fp16 [M, ldp].
 // One CTA per row.                                                                 vae.py:246-257
 // --------------------------------------------------------------------------------------------
@@ -1417,6 +1465,22 @@ extern "C" int mv_vae_latent_out(const void* head_cl, const float* W1, const flo
   vae_latent_out_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(head_cl), W1, b1, mean, inv_std, mu, Z, nvox, mu_plane, mu_off);
   MV_CHECK_LAUNCH("vae_latent_out_kernel");
+  return MV_OK;
+}
+
+extern "C" int mv_vae_head_gather(const void* d_cur, const void* d_prev, int kprev, int n, int H, int W,
+                                  const float* bias3_host, float* video, int64_t plane, int64_t frame_off,
+                                  mv_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != MV_OK) return rc;
+  MV_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0 && kprev >= 0 && kprev <= 2 && (kprev == 0 || d_prev != nullptr) &&
+                 frame_off >= 0 && frame_off + static_cast<int64_t>(n) * H * W <= plane,
+             "mv_vae_head_gather: bad shape (n=%d H=%d W=%d kprev=%d)", n, H, W, kprev);
+  dim3 grid((W + 31) / 32, (H + 7) / 8, n);
+  vae_head_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(d_cur), reinterpret_cast<const __half*>(d_prev), kprev, H, W, bias3_host[0],
+      bias3_host[1], bias3_host[2], video, plane, frame_off);
+  MV_CHECK_LAUNCH("vae_head_gather_kernel");
   return MV_OK;
 }
 

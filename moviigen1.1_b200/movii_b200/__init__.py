@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mv_vae_conv_strided": [_ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _int, _int, _int, _int, _int, _ptr, _int,
                             _int, _int, _int, _ptr],
     "mv_vae_video_in": [_ptr, _int, _int, _int, _int, _int, _ptr, _ptr],
+    "mv_vae_head_gather": [_ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr, _i64, _i64, _ptr],
     "mv_vae_latent_out": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _i64, _i64, _i64, _ptr],
     "mv_ipc_export": [_ptr, _ptr, _ptr, _ptr],
     "mv_ipc_open": [_ptr, _ptr],
@@ -411,6 +412,20 @@ def vae_conv_strided(x, conv, out, stride=(1, 2, 2), t_off=0):
     _call("mv_vae_conv_strided", _p(x), Tin, H, W, Cin, _p(conv.w), _p(conv.b), _p(out), T, Ho, Wo, Co, conv.ntaps,
           conv.taps.data_ptr(), int(t_off), st, sh, sw, _stream())
     return out
+
+
+def vae_head_gather(d_cur, d_prev, bias3, video, t0):
+    """d_cur [n,H,W,112] fp16 (+ d_prev [k<=2,H,W,112] or None) -> video[:, t0:t0+n] fp32 [3,T,H,W]; bias3: 3 python floats."""
+    _req(d_cur, torch.float16, "d_cur"); _req(d_prev, torch.float16, "d_prev"); _req(video, torch.float32, "video")
+    assert d_cur.dim() == 4 and d_cur.shape[3] == 112 and d_cur.is_contiguous() and video.is_contiguous()
+    n, H, W, _ = d_cur.shape
+    k = 0 if d_prev is None else d_prev.shape[0]
+    assert d_prev is None or (d_prev.is_contiguous() and tuple(d_prev.shape[1:]) == (H, W, 112) and k <= 2)
+    assert video.dim() == 4 and video.shape[0] == 3 and tuple(video.shape[2:]) == (H, W) and t0 + n <= video.shape[1]
+    arr = (_c.c_float * 3)(*[float(v) for v in bias3])
+    _call("mv_vae_head_gather", _p(d_cur), _p(d_prev), k, n, H, W, arr, _p(video), video.shape[1] * H * W, int(t0) * H * W,
+          _stream())
+    return video
 
 
 def vae_video_in(video, t0, n, out):

@@ -234,6 +234,16 @@ class VaeEngine:
         self.operand_dtype = "f16"
         self.head_gamma = f32(d.head[0].gamma.reshape(-1))
         self.head = _Conv(d.head[2].weight, d.head[2].bias, _taps(3, 3, 3), dev, cout_pad=16)
+        # The same head conv as ONE 1x1x1 conv to 27 taps x (3 + 1 pad) partial sums per voxel + a gather over the 27
+        # neighbours (mv_vae_head_gather): 6 MMAs per voxel tile instead of 162 sixteen-column ones (the 16-wide conv ran
+        # at 219 TFLOP/s executed, 4.5 % of the decode).  MOVII_VAE_HEAD=conv keeps the direct conv (A/B).
+        wh = d.head[2].weight.detach().to(F32)                                     # [3, C, 3, 3, 3]
+        wt = wh.new_zeros(27, 4, wh.shape[1])
+        wt[:, :3] = wh.reshape(3, wh.shape[1], 27).permute(2, 0, 1)                # [tap, co, c]
+        wt = torch.cat([wt.reshape(108, wh.shape[1]), wh.new_zeros(4, wh.shape[1])])    # 112 rows (multiple of 16)
+        self.head_taps = _Conv(wt.reshape(112, wh.shape[1], 1, 1, 1), None, _taps(1, 1, 1), dev)
+        self.head_bias = [float(v) for v in d.head[2].bias.detach().to(F32).cpu()]
+        self.head_mode = os.environ.get("MOVII_VAE_HEAD", "gather")
         # temporal chunk (latent frames per pass): the decoder is a causal network, every temporal conv carries the
         # last two frames of its input to the next chunk — the reference's feature cache (vae.py:28-36,205-217) with
         # chunks of `chunk` latent frames instead of one.  Bounds the live activations (1080P: 3 stage-D tensors of
@@ -424,9 +434,22 @@ class VaeEngine:
                 else:
                     a, k = a_in
                 del x, a_in
-                self.commit("head", a)
-                mv.vae_conv(a, self.head, video, res=None, out_mode=1, o_base=t_done * H * W, os_t=Tout * H * W, t_off=k)
-                del a
+                if self.head_mode == "gather":
+                    assert k == 0                                   # the temporal history lives in D, not in the input
+                    D = self.conv(a, self.head_taps)                # [nt, H, W, 112] partial sums per (tap, channel)
+                    del a
+                    prev = self.cache.get("head.D")
+                    mv.vae_head_gather(D, prev, self.head_bias, video, t_done)
+                    if nt >= 2 or prev is None:
+                        self.cache["head.D"] = D[-2:].clone()
+                    else:
+                        self.cache["head.D"] = torch.cat([prev[-1:], D])
+                    del D, prev
+                else:
+                    self.commit("head", a)
+                    mv.vae_conv(a, self.head, video, res=None, out_mode=1, o_base=t_done * H * W, os_t=Tout * H * W,
+                                t_off=k)
+                    del a
                 t_done += nt
         finally:
             self.cache = {}

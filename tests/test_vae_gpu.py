@@ -203,6 +203,48 @@ def test_vae_fused_epilogue_single_pass_matches_two_pass(shape, pair, with_res):
         assert torch.equal(raw0, raw1)
     assert (n0 - n1).abs().max().item() <= 2e-3 * max(1.0, n0.abs().max().item()), (n0 - n1).abs().max().item()
 
+def test_vae_head_gather_matches_direct_conv(vae):
+    """The head conv as a 1x1x1 conv to 27 x 4 partial sums + neighbour gather (mv_vae_head_gather) vs the direct 16-column
+    3x3x3 conv: same fp16 operands; the gather rounds the 27 partial sums to fp16 before adding them in fp32 (2^-12
+    relative each).  Also chunk = 1 (one-frame first chunk, D history of one frame) against the whole-sequence pass."""
+    import torch.nn.functional as F
+    import movii_b200 as mv
+    m, g = vae
+    eng = m.engine()
+    rec = g["cases"][(3, 4, 6)]
+    z = rec["z"].to(DEV)
+    keep_mode, keep_chunk = eng.head_mode, eng.chunk
+    try:
+        eng.head_mode = "conv"
+        direct = eng.decode(z).clone()
+        eng.head_mode = "gather"
+        gathered = eng.decode(z).clone()
+        eng.chunk = 1
+        assert torch.equal(eng.decode(z), gathered)
+    finally:
+        eng.head_mode, eng.chunk = keep_mode, keep_chunk
+    assert (direct - gathered).abs().max().item() <= 2e-3, (direct - gathered).abs().max().item()
+    assert (gathered.cpu() - rec["y"].float()).abs().max().item() <= 1e-2
+    # kernel level: random partial sums, d_prev with one frame, ragged H x W, against the same gather in torch
+    gen = torch.Generator().manual_seed(11)
+    n, H, W = 3, 11, 37
+    D = (torch.randn(1 + n, H, W, 112, generator=gen) * 0.2).half()
+    bias = [0.1, -0.2, 0.3]
+    video = torch.full((3, 5, H, W), float("nan"), device=DEV)
+    mv.vae_head_gather(D[1:].contiguous().to(DEV), D[:1].contiguous().to(DEV), bias, video, 2)
+    Dp = F.pad(D.float(), (0, 0, 1, 1, 1, 1, 1, 0))                       # zero frame before d_prev, spatial zero ring
+    ref = torch.zeros(3, n, H, W)
+    for it in range(3):
+        for ih in range(3):
+            for iw in range(3):
+                tap = (it * 3 + ih) * 3 + iw
+                ref += Dp[it:it + n, ih:ih + H, iw:iw + W, 4 * tap:4 * tap + 3].permute(3, 0, 1, 2)
+    ref = (ref + torch.tensor(bias).view(3, 1, 1, 1)).clamp(-1, 1)
+    assert torch.isnan(video[:, :2]).all()
+    assert (video[:, 2:].cpu() - ref).abs().max().item() <= 1e-5
+
+
+
 # ---- encoder (SURVEY.md §8f-4) ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", [(1, 16, 24), (5, 24, 40), (9, 16, 16), (13, 32, 16)])
 def test_vae_encode_matches_reference_golden(vae_enc, case, conv_kernel):
