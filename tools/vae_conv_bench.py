@@ -61,6 +61,20 @@ def main():
             mv.vae_conv_config(-2, -2)
             print(json.dumps(rec), flush=True)
             continue
+        if st == "head":       # the decoder head: 1x1x1 conv 96 -> 27 x 4 partial sums + neighbour gather vs the direct 16-column conv
+            T, H, W, Ci = 16, 832, 1920, 96
+            x = torch.randn(T, H, W, Ci, device=DEV, generator=g).half()
+            wt = torch.randn(112, Ci, 1, 1, 1, device=DEV, generator=g) / math.sqrt(Ci)
+            c1 = _Conv(wt.cpu(), None, _taps(1, 1, 1), DEV)
+            D = torch.empty(T, H, W, 112, dtype=torch.float16, device=DEV)
+            video = torch.empty(3, T, H, W, device=DEV)
+            ms1 = timeit(lambda: mv.vae_conv(x, c1, D, o_base=0, os_t=H * W * 112, os_h=W * 112, os_w=112))
+            ms2 = timeit(lambda: mv.vae_head_gather(D, None, [0.0, 0.0, 0.0], video, 0))
+            gb1 = T * H * W * (Ci + 112) * 2 / 1e9
+            gb2 = (T * H * W * 112 * 2 + 3 * T * H * W * 4) / 1e9
+            print(json.dumps(dict(kind="vae_head", shape=[T, H, W, Ci], conv1x1_ms=round(ms1, 3), conv1x1_gbs=round(gb1 / ms1 * 1e3, 1),
+                                  gather_ms=round(ms2, 3), gather_gbs=round(gb2 / ms2 * 1e3, 1))), flush=True)
+            continue
         if st.startswith("X:"):      # custom shape X:T:H:W:Cin:Cout (experiments on what bounds a channel plan)
             T, H, W, Ci, Co = (int(v) for v in st.split(":")[1:])
         else:
