@@ -768,24 +768,24 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int wset = (warp - 2) >> 2;
     const int quad = pw & 3;
     const int r = quad * 32 + lane;
+    const int half0 = ((p.BN + 63) >> 6) << 5;     // split tiles: set 0 takes whole 32-column chunks covering >= half the row
     int it = 0;
     for (int st = pair_id; st < q.num_super; st += num_pairs, ++it) {
       const int buf = it % nbuf;
       const uint32_t use = static_cast<uint32_t>(it / nbuf);
       int n_blk, t, h0, w0;
       decode(st, n_blk, t, h0, w0);
-      if (split) conv_prefetch_res(p, n_blk, t, h0 + (r >> 4), w0 + (r & 15), wset * (p.BN >> 1), p.BN >> 1);
+      if (split) conv_prefetch_res(p, n_blk, t, h0 + (r >> 4), w0 + (r & 15), wset * half0, wset == 0 ? half0 : p.BN - half0);
       else
         for (int j = wset; j < NT; j += 2) conv_prefetch_res(p, n_blk, t, h0 + j * kConvTH + (r >> 4), w0 + (r & 15), 0, p.BN);
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after();
       if (split) {
-        const int half = p.BN >> 1;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
         float* mine = ssx + ((it & 1) * 2 + wset) * 128 + r;
         const float* other = ssx + ((it & 1) * 2 + (wset ^ 1)) * 128 + r;
-        conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15), &tempty[buf], 0, wset * half, half,
-                           p.norm_out != nullptr ? mine : nullptr, other);
+        conv_epilogue_tile(p, taddr, n_blk, t, h0 + (r >> 4), w0 + (r & 15), &tempty[buf], 0, wset * half0,
+                           wset == 0 ? half0 : p.BN - half0, p.norm_out != nullptr ? mine : nullptr, other);
         continue;
       }
       for (int j = wset; j < NT; j += 2) {
@@ -1230,7 +1230,10 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
   MV_REQUIRE(out != nullptr || norm_out != nullptr, "mv_vae_conv: no output");
 
   // ---- CTA-pair kernel (conv_igemm_pair_kernel) for the tensor-bound convolutions -----------------------------------
-  if (conv_pair_enabled() && !strided && (BK == 64 || BK == 32) && BN % 16 == 0 && ntaps >= 2) {
+  // (1x1x1 convs too: their tiles are all epilogue — 6 MMAs for 128 x 224 B of stores in the decoder's head — and the
+  // pair kernel has two epilogue warp sets per CTA where the single-CTA kernel has one: ncu showed that one warp per
+  // scheduler, not DRAM (2.6 TB/s), bounds them)
+  if (conv_pair_enabled() && !strided && (BK == 64 || BK == 32) && BN % 16 == 0 && (ntaps >= 2 || Cin >= 64)) {
     Conv2Params q;
     memset(&q, 0, sizeof(q));
     bool ok = true;
@@ -1284,8 +1287,8 @@ static int vae_conv_impl(const void* in_cl, int in_T, int in_H, int in_W, int Ci
       q.nbuf = (2 * nt * BN <= 512) ? 2 : 1;
       // one tile per CTA leaves the second epilogue warp set idle: let both drain the tile, half of the columns each
       // (plain epilogue: any BN that halves into 32-column chunks; fused norm: 192 = 2 x 96 register-resident halves)
-      q.split_cols = (nt == 1 && BN % 64 == 0 && out_mode == 0 && conv_split_enabled() &&
-                      (norm_out == nullptr || (conv_epi_regs() && BN == 192))) ? 1 : 0;
+      q.split_cols = (nt == 1 && BN >= 64 && out_mode == 0 && conv_split_enabled() &&
+                      (norm_out == nullptr ? true : (conv_epi_regs() && BN == 192))) ? 1 : 0;
       q.sup_h = (out_H + 2 * nt * kConvTH - 1) / (2 * nt * kConvTH);
       q.sup_w = (out_W + kConvTW - 1) / kConvTW;
       const int num_n = Cout / BN;

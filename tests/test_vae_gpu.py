@@ -203,6 +203,39 @@ def test_vae_fused_epilogue_single_pass_matches_two_pass(shape, pair, with_res):
         assert torch.equal(raw0, raw1)
     assert (n0 - n1).abs().max().item() <= 2e-3 * max(1.0, n0.abs().max().item()), (n0 - n1).abs().max().item()
 
+@pytest.mark.parametrize("shape", [(3, 19, 37, 96, 112), (2, 24, 40, 192, 384), (2, 17, 33, 384, 1152), (2, 9, 20, 64, 80)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_vae_conv_1x1x1_pair_matches_single_cta(shape, with_res):
+    """1x1x1 convs (head partial sums, shortcuts, attention qkv / proj) on the CTA-pair kernel — two epilogue warp sets,
+    columns of a one-tile accumulator split 64 | rest — against the single-CTA kernel and torch."""
+    import movii_b200 as mv
+    from wan.modules.vae import _Conv, _taps
+    T, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = torch.randn(T, H, W, Ci, generator=g).half()
+    wt = torch.randn(Co, Ci, 1, 1, 1, generator=g) / math.sqrt(Ci)
+    b = 0.1 * torch.randn(Co, generator=g)
+    c = _Conv(wt, b, _taps(1, 1, 1), DEV)
+    res = torch.randn(T, H, W, Co, generator=g).half() if with_res else None
+    outs = []
+    for pair in (0, 1):
+        mv.vae_conv_config(pair, 0)
+        try:
+            out = torch.full((T, H, W, Co), float("nan"), dtype=torch.float16, device=DEV)
+            mv.vae_conv(x.to(DEV), c, out, res=None if res is None else res.to(DEV), o_base=0, os_t=H * W * Co, os_h=W * Co,
+                        os_w=Co)
+            torch.cuda.synchronize()
+        finally:
+            mv.vae_conv_config(-2, -2, -2)
+        outs.append(out.float().cpu())
+    ref = x.float().reshape(-1, Ci) @ V.f16_rt(wt.reshape(Co, Ci)).t() + b
+    ref = ref.reshape(T, H, W, Co) + (0 if res is None else res.float())
+    for o in outs:
+        assert torch.isfinite(o).all()
+        assert (o - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+    assert (outs[0] - outs[1]).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_vae_head_gather_matches_direct_conv(vae):
     """The head conv as a 1x1x1 conv to 27 x 4 partial sums + neighbour gather (mv_vae_head_gather) vs the direct 16-column
     3x3x3 conv: same fp16 operands; the gather rounds the 27 partial sums to fp16 before adding them in fp32 (2^-12
