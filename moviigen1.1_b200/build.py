@@ -41,14 +41,17 @@ def _compile(src, force, verbose):
     obj = os.path.join(OBJDIR, src[:-3] + ".o")
     stamp = obj + ".sha"
     dig = _digest(src)
+    plog = obj + ".ptxas.log"       # per-source -Xptxas -v output, so lib/ptxas.log always covers every kernel
     if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return obj, False, ""
+        return obj, False, open(plog).read() if os.path.exists(plog) else ""
     cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
     with open(stamp, "w") as fh:
         fh.write(dig)
+    with open(plog, "w") as fh:
+        fh.write(r.stderr)
     return obj, True, r.stderr
 
 
