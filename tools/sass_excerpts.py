@@ -28,7 +28,6 @@ KERNELS = [
     ("conv_igemm BK=16 (16-channel stems)", "vae_conv_sm100.o", r"conv_igemm_kernelILi16ELb0E", 3),
     ("rmsnorm_silu_cl (WanVAE)", "vae_conv_sm100.o", r"rmsnorm_silu_cl_kernelILi32ELi1E", 2),
     ("softmax_rows_reg (WanVAE attention, register-resident row)", "vae_conv_sm100.o", r"softmax_rows_reg_kernel", 3),
-    ("conv_epilogue_fused_regs (single-pass RMS_norm+SiLU epilogue, noinline)", "vae_conv_sm100.o", r"conv_epilogue_fused_regs", 3),
     ("vae_head_gather (decoder head: 27-neighbour gather of partial sums)", "vae_conv_sm100.o", r"vae_head_gather_kernel", 2),
     ("vae_latent_in", "vae_conv_sm100.o", r"vae_latent_in_kernel", 1),
     ("vae_video_in (encoder)", "vae_conv_sm100.o", r"vae_video_in_kernel", 1),
