@@ -102,6 +102,7 @@ def _check(rc, what):
 
 
 LAUNCHES = 0          # kernels launched through the C ABI by this process (bench.py reports it)
+CONFIG_EPOCH = 0      # bumped by every *_config() call: captured CUDA graphs are keyed on it (a graph bakes the variant in)
 _TIMED = {}           # entry point -> list of (start_event, end_event); filled while enabled via time_kernels()
 
 
@@ -126,6 +127,16 @@ def _call(name, *args):
         rc = getattr(lib(), name)(*args)
     LAUNCHES += 1
     _check(rc, name)
+
+
+def count_replayed_launches(n):
+    """A CUDA-graph replay launches the n kernels that were captured through _call(): keep LAUNCHES truthful."""
+    global LAUNCHES
+    LAUNCHES += int(n)
+
+
+def timing_enabled():
+    return bool(_TIMED)
 
 
 def _p(t):
@@ -592,11 +603,15 @@ def attention_trace(q, k, v, out, trace, softmax_scale=None):
 
 def roles_config(hi=-1):
     """Diagnostics: 1 = TMA / MMA role warps at the highest warp ids of every tcgen05 kernel, 0 = lowest."""
+    global CONFIG_EPOCH
+    CONFIG_EPOCH += 1
     _check(lib().mv_roles_config(int(hi)), "mv_roles_config")
 
 
 def gemm_config(pair=-1):
     """Diagnostics: 1 = CTA-pair (cta_group::2) GEMM kernel for the large linears, 0 = single-CTA kernel."""
+    global CONFIG_EPOCH
+    CONFIG_EPOCH += 1
     _check(lib().mv_gemm_config(int(pair)), "mv_gemm_config")
 
 
@@ -604,11 +619,15 @@ def vae_conv_config(pair=-1, tiles_per_cta=-1, epi_regs=-1):
     """Diagnostics: pair 1 = CTA-pair convolution kernel for the tensor-bound WanVAE convs, 0 = single-CTA kernel;
     tiles_per_cta 0 = automatic, 1 | 2 | 4 forced; epi_regs 1 = fused norm epilogue in one TMEM pass (row kept in
     registers), 0 = two passes; -1 keeps, -2 restores the default."""
+    global CONFIG_EPOCH
+    CONFIG_EPOCH += 1
     _check(lib().mv_vae_conv_config(int(pair), int(tiles_per_cta), int(epi_regs)), "mv_vae_conv_config")
 
 
 def attention_config(kstep=-1, emu=-1, stale=-1, pingpong=-1, skew=-1, wait_spin=-1, pack=-1):
     """Diagnostics: pick the attention kernel variant for subsequent launches (negative = keep); tools/ab_step.py."""
+    global CONFIG_EPOCH
+    CONFIG_EPOCH += 1
     _check(lib().mv_attention_config(int(kstep), int(emu), int(stale), int(pingpong), int(skew), int(wait_spin),
                                        int(pack)),
            "mv_attention_config")

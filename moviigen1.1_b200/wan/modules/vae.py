@@ -252,6 +252,8 @@ class VaeEngine:
         self.cache = {}
         # A/B switch (tools/vae_bench.py): 0 = the block's last conv does not emit the consumer's norm (stand-alone pass)
         self.fuse_c6 = os.environ.get("MOVII_VAE_FUSE_C6", "1") != "0"
+        self.use_graph = os.environ.get("MOVII_VAE_GRAPH", "1") != "0"
+        self._graphs = {}
         self.model = model
         self.enc = None              # encoder plan, packed on the first encode()
 
@@ -392,7 +394,40 @@ class VaeEngine:
 
     # -- WanVAE.decode for one latent ---------------------------------------------------------------------------
     def decode(self, z):
-        """z [z_dim, T, h, w] fp32 -> [3, 1+4(T-1), 8h, 8w] fp32 in [-1, 1]."""
+        """z [z_dim, T, h, w] fp32 -> [3, 1+4(T-1), 8h, 8w] fp32 in [-1, 1].
+
+        The ~570 launches + ~150 device copies of one decode are captured in a CUDA graph per (latent shape, chunking)
+        on the second decode of that shape and replayed afterwards: same kernels, same order, no host work between them
+        (MOVII_VAE_GRAPH=0: direct launches every time)."""
+        if not self.use_graph or mv.timing_enabled():
+            return self._decode(z)
+        key = (tuple(z.shape), self.chunk, self.head_mode, self.fuse_c6, mv.CONFIG_EPOCH)
+        ent = self._graphs.get(key)
+        if ent is None:                                    # first decode of this shape: direct launches (also warms up)
+            self._graphs[key] = "seen"
+            return self._decode(z)
+        if ent == "seen":
+            try:
+                static_z = z.detach().to(self.device, F32).contiguous().clone()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0 = mv.LAUNCHES
+                with torch.cuda.graph(graph):
+                    static_out = self._decode(static_z)
+                ent = (graph, static_z, static_out, mv.LAUNCHES - l0)
+                self._graphs[key] = ent
+            except Exception as ex:                           # capture refused: keep launching directly (same kernels)
+                logging.warning("WanVAE.decode: CUDA graph capture failed (%r); using direct launches", ex)
+                self.use_graph = False
+                self.cache = {}
+                return self._decode(z)
+        graph, static_z, static_out, n_launch = ent
+        static_z.copy_(z)
+        graph.replay()
+        mv.count_replayed_launches(n_launch)
+        return static_out.clone()
+
+    def _decode(self, z):
         Z, T, h, w = z.shape
         z = z.to(self.device, F32).contiguous()
         n_up3d = sum(1 for kind, p in self.layers if kind == "up" and p["mode"] == "upsample3d")
