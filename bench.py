@@ -468,7 +468,7 @@ def main():
             vae.decode([zlat])                      # warm-up 1: direct launches (sizes the allocator; peak memory is read here)
             torch.cuda.synchronize()
             vae_peak = torch.cuda.max_memory_allocated(dev) - base_mem
-            vae.decode([zlat])                      # warm-up 2: the decode of this shape is captured in a CUDA graph
+            vae.decode([zlat])                      # warm-up 2 (MOVII_VAE_GRAPH=1: the decode of this shape is captured here)
             torch.cuda.synchronize()
             v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0v = mv.LAUNCHES

@@ -237,31 +237,32 @@ def test_vae_conv_1x1x1_pair_matches_single_cta(shape, with_res):
 
 
 def test_vae_decode_cuda_graph_replay_is_bit_identical(vae):
-    """The second decode of a latent shape is captured in a CUDA graph, later ones replay it: same bits as the direct
+    """MOVII_VAE_GRAPH=1: the second decode of a latent shape is captured in a CUDA graph, later ones replay it: same bits as the direct
     launches, the launch counter keeps counting, a different latent of the same shape gives ITS result (static input)."""
     import movii_b200 as mv
     m, g = vae
     eng = m.engine()
-    assert eng.use_graph
     z = g["cases"][(3, 4, 6)]["z"].to(DEV)
-    eng._graphs.clear()
-    l0 = mv.LAUNCHES
-    direct = eng.decode(z).clone()
-    per_decode = mv.LAUNCHES - l0
-    captured = eng.decode(z).clone()                       # capture (kernels do not run) + first replay
-    l1 = mv.LAUNCHES
-    replayed = eng.decode(z).clone()
-    assert mv.LAUNCHES - l1 == per_decode
-    assert any(isinstance(v, tuple) for v in eng._graphs.values())
-    assert torch.equal(direct, captured) and torch.equal(direct, replayed)
-    z2 = torch.roll(z, 1, dims=-1)
     keep = eng.use_graph
     try:
+        eng.use_graph = True                                   # opt-in (MOVII_VAE_GRAPH=1)
+        eng._graphs.clear()
+        l0 = mv.LAUNCHES
+        direct = eng.decode(z).clone()
+        per_decode = mv.LAUNCHES - l0
+        captured = eng.decode(z).clone()                       # capture (kernels do not run) + first replay
+        l1 = mv.LAUNCHES
+        replayed = eng.decode(z).clone()
+        assert mv.LAUNCHES - l1 == per_decode
+        assert any(isinstance(v, tuple) for v in eng._graphs.values())
+        assert torch.equal(direct, captured) and torch.equal(direct, replayed)
+        z2 = torch.roll(z, 1, dims=-1)
         out_graph = eng.decode(z2).clone()
         eng.use_graph = False
         out_direct = eng.decode(z2)
     finally:
         eng.use_graph = keep
+        eng._graphs.clear()
     assert torch.equal(out_graph, out_direct) and not torch.equal(out_graph, direct)
 
 

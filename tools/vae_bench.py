@@ -77,7 +77,7 @@ def main():
     vae = WanVAE(vae_pth=None, device="cuda")
     z = torch.randn(16, T, h, w, device="cuda")
     out = vae.decode([z])[0]  # warm-up (also builds the engine)
-    out = vae.decode([z])[0]  # second warm-up: this shape is captured in a CUDA graph (MOVII_VAE_GRAPH=0: direct launches)
+    out = vae.decode([z])[0]  # second warm-up: with MOVII_VAE_GRAPH=1 this shape is captured in a CUDA graph here
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
