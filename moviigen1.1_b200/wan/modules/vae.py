@@ -203,6 +203,16 @@ def _parity_convs(weight, bias, device):
     return out
 
 
+def _head_tap_matrix(weight):
+    """Head conv weight [3, C, 3, 3, 3] -> [112, C]: row 4*tap + co = W[co, :, tap] (tap in weight order (kt, kh, kw), co < 3;
+    the fourth row of every tap and rows 108..111 are zero).  x @ rows gives, per voxel, the 27 x 3 partial sums that
+    mv_vae_head_gather adds over the voxel's neighbours."""
+    wh = weight.detach().to(F32)
+    wt = wh.new_zeros(27, 4, wh.shape[1])
+    wt[:, :3] = wh.reshape(3, wh.shape[1], 27).permute(2, 0, 1)                    # [tap, co, c]
+    return torch.cat([wt.reshape(108, wh.shape[1]), wh.new_zeros(4, wh.shape[1])])   # 112 rows (a multiple of 16)
+
+
 class VaeEngine:
     def __init__(self, model):
         dev = model.conv2.weight.device
@@ -237,11 +247,8 @@ class VaeEngine:
         # The same head conv as ONE 1x1x1 conv to 27 taps x (3 + 1 pad) partial sums per voxel + a gather over the 27
         # neighbours (mv_vae_head_gather): 6 MMAs per voxel tile instead of 162 sixteen-column ones (the 16-wide conv ran
         # at 219 TFLOP/s executed, 4.5 % of the decode).  MOVII_VAE_HEAD=conv keeps the direct conv (A/B).
-        wh = d.head[2].weight.detach().to(F32)                                     # [3, C, 3, 3, 3]
-        wt = wh.new_zeros(27, 4, wh.shape[1])
-        wt[:, :3] = wh.reshape(3, wh.shape[1], 27).permute(2, 0, 1)                # [tap, co, c]
-        wt = torch.cat([wt.reshape(108, wh.shape[1]), wh.new_zeros(4, wh.shape[1])])    # 112 rows (multiple of 16)
-        self.head_taps = _Conv(wt.reshape(112, wh.shape[1], 1, 1, 1), None, _taps(1, 1, 1), dev)
+        wt = _head_tap_matrix(d.head[2].weight)
+        self.head_taps = _Conv(wt.reshape(112, wt.shape[1], 1, 1, 1), None, _taps(1, 1, 1), dev)
         self.head_bias = [float(v) for v in d.head[2].bias.detach().to(F32).cpu()]
         self.head_mode = os.environ.get("MOVII_VAE_HEAD", "gather")
         # temporal chunk (latent frames per pass): the decoder is a causal network, every temporal conv carries the

@@ -193,3 +193,30 @@ def test_tokenizer_cleaning_matches_reference_semantics():
     assert tk.basic_clean(" &amp;amp; x ") == "& x"
     assert tk.canonicalize("Hello_World, it's  ME!") == "hello world its me"
     assert tk.canonicalize("a.b|c.d", keep_punctuation_exact_string="|") == "ab|cd"
+
+
+def test_vae_head_conv_equals_tap_matrix_plus_gather():
+    """Host logic of the decoder head (wan/modules/vae.py::_head_tap_matrix + csrc vae_head_gather_kernel): the causal
+    3x3x3 conv 96 -> 3 equals ONE per-voxel matrix product to 27 x (3 + 1 pad) partial sums followed by the sum of each
+    output voxel's 27 neighbours' partials (zero outside the image and before the first frame)."""
+    import torch.nn.functional as F
+    from oracle import vae_oracle as V
+    from wan.modules.vae import _head_tap_matrix
+    g = torch.Generator().manual_seed(21)
+    C, T, H, W = 96, 4, 5, 7
+    w, b = torch.randn(3, C, 3, 3, 3, generator=g) / 50, torch.randn(3, generator=g)
+    x = torch.randn(1, C, T, H, W, generator=g)
+    ref = V.causal_conv3d(x, w, b)[0]                                            # [3, T, H, W]
+    wt = _head_tap_matrix(w)
+    assert wt.shape == (112, C) and torch.count_nonzero(wt[3::4]) == 0 and torch.count_nonzero(wt[108:]) == 0
+    D = x[0].permute(1, 2, 3, 0) @ wt.t()                                        # [T, H, W, 112]
+    Dp = F.pad(D, (0, 0, 1, 1, 1, 1, 2, 0))                                      # two zero frames in front, zero ring
+    out = torch.zeros(3, T, H, W)
+    for it in range(3):
+        for ih in range(3):
+            for iw in range(3):
+                tap = (it * 3 + ih) * 3 + iw
+                out += Dp[it:it + T, ih:ih + H, iw:iw + W, 4 * tap:4 * tap + 3].permute(3, 0, 1, 2)
+    out += b.view(3, 1, 1, 1)
+    assert (out - ref).abs().max().item() <= 1e-5
+
