@@ -184,10 +184,11 @@ class _Conv:
         self.ntaps = len(taps)
 
 
-def _parity_convs(weight, bias, device):
+def _parity_weights(weight):
     """nearest-exact x2 followed by a 3x3 Conv2d == four 2x2 convolutions on the low-res grid, one per output
     parity (a, b) (vae.py:74-79).  Rows 2h+a-1, 2h+a, 2h+a+1 of the upsampled image are source rows
-    {h-1, h, h} (a=0) or {h, h, h+1} (a=1); the kernel rows falling on the same source row are summed (in fp32)."""
+    {h-1, h, h} (a=0) or {h, h, h+1} (a=1); the kernel rows falling on the same source row are summed (in fp32).
+    Returns {(a, b): (taps [(0, dh, dw)] * 4, weight [Co, Ci, 4, 1, 1])}."""
     groups = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
     w = weight.detach().to(F32)                                                               # [Co, Ci, 3, 3]
     out = {}
@@ -198,9 +199,12 @@ def _parity_convs(weight, bias, device):
                 for dw, kws in groups[b]:
                     taps.append((0, dh, dw))
                     mats.append(sum(w[:, :, kh, kw] for kh in khs for kw in kws))
-            wp = torch.stack(mats, dim=2).unsqueeze(-1).unsqueeze(-1)                       # [Co, Ci, 4, 1, 1]
-            out[(a, b)] = _Conv(wp, bias, taps, device)
+            out[(a, b)] = (taps, torch.stack(mats, dim=2).unsqueeze(-1).unsqueeze(-1))      # [Co, Ci, 4, 1, 1]
     return out
+
+
+def _parity_convs(weight, bias, device):
+    return {ab: _Conv(wp, bias, taps, device) for ab, (taps, wp) in _parity_weights(weight).items()}
 
 
 def _head_tap_matrix(weight):

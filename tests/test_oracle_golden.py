@@ -220,3 +220,24 @@ def test_vae_head_conv_equals_tap_matrix_plus_gather():
     out += b.view(3, 1, 1, 1)
     assert (out - ref).abs().max().item() <= 1e-5
 
+
+def test_vae_subpixel_upsample_weights_equal_upsample_then_conv():
+    """Host logic of Resample 'upsample2d/3d' (wan/modules/vae.py::_parity_weights): nearest-exact x2 + Conv2d(3x3, pad 1)
+    equals four 2x2 convolutions on the low-resolution image, one per output parity, with the kernel rows / columns that
+    land on the same source pixel pre-summed."""
+    import torch.nn.functional as F
+    from wan.modules.vae import _parity_weights
+    g = torch.Generator().manual_seed(22)
+    Ci, Co, H, W = 8, 4, 5, 7
+    w, b = torch.randn(Co, Ci, 3, 3, generator=g), torch.randn(Co, generator=g)
+    x = torch.randn(2, Ci, H, W, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=(2.0, 2.0), mode="nearest-exact"), w, b, padding=1)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for (a, bb), (taps, wp) in _parity_weights(w).items():
+        acc = b.view(1, Co, 1, 1).expand(2, Co, H, W).clone()
+        for i, (_, dh, dw) in enumerate(taps):
+            acc += torch.einsum("nchw,oc->nohw", xp[:, :, 1 + dh:1 + dh + H, 1 + dw:1 + dw + W], wp[:, :, i, 0, 0])
+        out[:, :, a::2, bb::2] = acc
+    assert (out - ref).abs().max().item() <= 1e-5
+
