@@ -23,6 +23,7 @@ the kept rows are identical.  There is no CPU path: `t5_cpu=True` callers still 
 The T5 decoder / seq2seq model is never instantiated by the reference pipeline (`encoder_only=True`, t5.py:490) and
 is not built.
 """
+import os
 import logging
 import math
 
@@ -136,6 +137,11 @@ class T5Engine:
         self.final_w = enc.norm.weight.detach().float().contiguous()
         self._bias = {}
         self._ws = {}
+        # One encode = 266 launches of ~20 us kernels: the Python / ctypes launch path (~20 us per call) is as long as the
+        # kernels, so the second encode of a (rows, valid keys) shape is captured in a CUDA graph and replayed afterwards
+        # (MOVII_T5_GRAPH=0: direct launches every time).
+        self.use_graph = os.environ.get("MOVII_T5_GRAPH", "1") != "0"
+        self._graphs = {}
 
     def bias_tables(self, L):
         if L not in self._bias:
@@ -163,9 +169,38 @@ class T5Engine:
     def forward(self, ids, kv_len=None):
         """ids: int64 [L] (L <= 512) on the device; keys >= kv_len are masked.  Returns bf16 [L, dim] (a workspace
         view: clone to keep it across calls)."""
-        enc = self.enc
         L = ids.numel()
         kv_len = L if kv_len is None else int(kv_len)
+        if not self.use_graph or mv.timing_enabled():
+            return self._forward(ids, kv_len)
+        key = (L, kv_len, mv.CONFIG_EPOCH)
+        ent = self._graphs.get(key)
+        if ent is None:                                    # first encode of this shape: direct launches (also warms up)
+            self._graphs[key] = "seen"
+            return self._forward(ids, kv_len)
+        if ent == "seen":
+            try:
+                static_ids = ids.contiguous().clone()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0 = mv.LAUNCHES
+                with torch.cuda.graph(graph):
+                    self._forward(static_ids, kv_len)
+                ent = (graph, static_ids, mv.LAUNCHES - l0)
+                self._graphs[key] = ent
+            except Exception as ex:                           # capture refused: keep launching directly (same kernels)
+                logging.warning("T5Engine: CUDA graph capture failed (%r); using direct launches", ex)
+                self.use_graph = False
+                return self._forward(ids, kv_len)
+        graph, static_ids, n_launch = ent
+        static_ids.copy_(ids)
+        graph.replay()
+        mv.count_replayed_launches(n_launch)
+        return self.workspace(L)["out"]
+
+    def _forward(self, ids, kv_len):
+        enc = self.enc
+        L = ids.numel()
         ws = self.workspace(L)
         x, n, qkv, a, f, g = ws["x"], ws["n"], ws["qkv"], ws["a"], ws["f"], ws["g"]
         A, H = enc.dim_attn, enc.num_heads
