@@ -8,7 +8,6 @@ Sequence parallelism (Ulysses, wan/distributed/xdit_context_parallel.py in the r
 `SeqParallel`: token rows are sharded across ranks, the self-attention core is computed per head group after
 an all-to-all (see wan/distributed/ulysses.py).
 """
-import math
 
 import torch
 

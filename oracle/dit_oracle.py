@@ -13,7 +13,6 @@ oracle/make_golden.py, and stored under tests/golden/ (tests/test_oracle_golden.
 reference: identity -> exact fp32 reference semantics on CPU; `bf16_rt` ->
 bf16-autocast semantics, the arithmetic contract of the CUDA kernels.
 """
-import math
 
 import torch
 import torch.nn.functional as F

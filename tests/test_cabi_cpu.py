@@ -1,6 +1,5 @@
 """CPU-side checks of the C-ABI library: it loads, exports every symbol include/movii_b200.h declares, and fails
 loudly (no fallback) when there is no B200."""
-import ctypes
 import os
 import re
 

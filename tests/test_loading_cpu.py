@@ -2,7 +2,6 @@
 exactly as the reference's ModelMixin.from_pretrained call (wan/text2video.py:87) expects them; WanVAE_ accepts a full
 reference VAE state dict (both halves)."""
 import json
-import os
 
 import pytest
 import torch

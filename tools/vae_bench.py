@@ -4,7 +4,6 @@ Prints one JSON line.  VAE FLOPs/bytes per SURVEY.md §8d (1080P: 1116.5 TF, 720
 import json
 import os
 import sys
-import time
 
 import torch
 
